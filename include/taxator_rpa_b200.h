@@ -1,0 +1,160 @@
+/*
+ * taxator_rpa_b200.h -- C ABI of the B200-native RPA (realignment placement algorithm) hot path.
+ *
+ * Drop-in boundary for fungs/taxator-tk's `taxator -a rpa`: everything below replaces, for a whole
+ * batch of query segments at once, what the reference does one segment at a time on a CPU thread in
+ *     RPAPredictionModel::predict()          core/src/taxonpredictionmodelsequence.hh:341-838
+ * i.e. the SeqAn pairwise alignments (hh:133-256), the reference/query segment fetch
+ * (hh:856-880, core/src/sequencestorage.hh:341-369,430-457, core/src/faidx.h:315-350) and the
+ * distance -> taxon-range reduction with LCA (core/src/taxonomyinterface.cpp:52-77).
+ * The reference has no FFI today (single C++ process); INTEGRATION.md shows the ~60-line
+ * RPAPredictionModel subclass a maintainer would add on the reference side to bind these symbols.
+ *
+ * Conventions: plain pointers and sizes, caller-owned HOST buffers unless a name says "dev";
+ * every function returns 0 on success and a negative code on failure, with a message available
+ * from trpa_last_error() (thread-local).  No C++ exceptions cross this boundary.  There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails with TRPA_ERR_CUDA.
+ * A context is bound to one GPU; use one context (one process or thread) per GPU.
+ */
+#ifndef TAXATOR_RPA_B200_H_
+#define TAXATOR_RPA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRPA_ABI_VERSION 1
+
+#define TRPA_OK 0
+#define TRPA_ERR_CUDA (-1)
+#define TRPA_ERR_ARG (-2)
+#define TRPA_ERR_STATE (-3)
+#define TRPA_ERR_NOMEM (-4)
+
+#define TRPA_NO_NODE 0xffffffffu
+
+typedef struct trpa_ctx trpa_ctx;
+
+/* Sequence alphabets.  NT: SeqAn Dna5 (A,C,G,T/U -> 0..3, anything else -> N, N==N matches),
+ * stored as 2-bit planes + N plane.  AA: SeqAn AminoAcid 27 letters (unknown -> X), 5 bit, 6/word. */
+#define TRPA_ALPHA_NT 0
+#define TRPA_ALPHA_AA 1
+
+/* Which store a sequence table is loaded into (taxator.cpp:230-249: query store / db store). */
+#define TRPA_STORE_QUERY 0
+#define TRPA_STORE_REF 1
+
+/* One alignment record of a segment == the fields of AlignmentRecordTaxonomy that predict() reads
+ * (core/src/alignmentrecord.hh:39-93,207-238).  Coordinates are 1-based inclusive; rstart > rstop
+ * means reverse strand (hh:872-879).  `node` indexes the arrays given to trpa_load_taxonomy. */
+typedef struct trpa_candidate {
+  uint32_t ref_seq;     /* ordinal in the reference store (refid2position_, sequencestorage.hh:347) */
+  uint32_t rstart, rstop;
+  uint32_t qstart, qstop;
+  float score;
+  uint32_t identities;
+  uint32_t alnlen;
+  uint32_t node;
+} trpa_candidate;
+
+/* One query segment == one record set handed to predict() (taxator.cpp:66-72,163-175), unmasked
+ * records only, in record-set order (the library applies SortFilter's stable sort itself). */
+typedef struct trpa_segment {
+  uint32_t query_seq;   /* ordinal in the query store */
+  uint32_t cand_begin;  /* first candidate of this segment in the candidate table */
+  uint32_t cand_count;
+  uint32_t reserved;
+} trpa_segment;
+
+#define TRPA_KIND_NONE 0      /* n==0: unclassified, hh:359-368 (ival left untouched by the reference) */
+#define TRPA_KIND_SINGLE 1    /* n==1: hh:371-388 */
+#define TRPA_KIND_IDENTICAL 2 /* full-length 100% hit shortcut: hh:431-472 */
+#define TRPA_KIND_PLACED 3    /* three-pass placement: hh:474-837 */
+
+/* == the PredictionRecord fields predict() sets (core/src/predictionrecord.hh:38-167) plus the
+ * STATS counters of hh:834-837. */
+typedef struct trpa_result {
+  uint32_t qrstart, qrstop;           /* query feature begin/end */
+  uint32_t lower_node, upper_node;    /* setNodeRange(lower, upper, support) */
+  uint32_t rtax_node;                 /* setBestReferenceTaxon */
+  uint32_t support;
+  float ival;                         /* setInterpolationValue; undefined for TRPA_KIND_NONE */
+  float signal;                       /* setSignalStrength (always 0, hh:722-725) */
+  uint32_t n_pass0, n_pass1, n_pass2; /* alignments computed per pass */
+  uint32_t kind;
+  uint64_t cells;                     /* sum |A|*|B| over those alignments (GCUPS numerator) */
+} trpa_result;
+
+/* Per-kernel device time accumulated since the last reset (CUDA events on the context's stream). */
+typedef struct trpa_profile {
+  double ms_edit_distance;  uint64_t launches_edit_distance;  uint64_t cells_edit_distance;
+  double ms_protein;        uint64_t launches_protein;        uint64_t cells_protein;
+  double ms_stage;          uint64_t launches_stage;          uint64_t bytes_stage;
+  double ms_decide;         uint64_t launches_decide;
+  double ms_other;          uint64_t launches_other;
+  uint64_t rounds;
+  uint64_t pairs;
+} trpa_profile;
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+int trpa_abi_version(void);
+const char* trpa_last_error(void);
+/* cuda_stream: a cudaStream_t to run on (e.g. torch's current stream), or NULL for an own stream. */
+trpa_ctx* trpa_create(int device, void* cuda_stream);
+void trpa_destroy(trpa_ctx* ctx);
+/* exclude_factor = taxator -x (default 0.5), toppercent = taxator -t (default 0.05); taxator.cpp:252 */
+int trpa_set_params(trpa_ctx* ctx, float exclude_factor, float toppercent);
+/* upper bound for the per-chunk staging arena in bytes (default: 1/4 of free HBM) */
+int trpa_set_arena_bytes(trpa_ctx* ctx, uint64_t bytes);
+int trpa_profile_reset(trpa_ctx* ctx);
+int trpa_profile_get(trpa_ctx* ctx, trpa_profile* out);
+
+/* ---- taxonomy: replaces TaxonomyInterface over TaxonTree (taxontree.hh:46-69) ------------- */
+/* parent[root] == root.  left/right are the nested-set values, depth = root_pathlength (< 64). */
+int trpa_load_taxonomy(trpa_ctx* ctx, const uint32_t* parent, const uint32_t* left, const uint32_t* right,
+                       const uint8_t* depth, uint32_t n_nodes, uint32_t root);
+
+/* ---- sequence stores: replace RandomInmemorySeqStoreRO / RandomIndexedSeqstoreRO ---------- */
+/* chars: the concatenated residue characters (FASTA payload without line breaks), off[i]/len[i] the
+ * start and length of sequence i.  Packed on the GPU into the HBM-resident store. */
+int trpa_load_store(trpa_ctx* ctx, int store, int alphabet, const char* chars, const uint64_t* off,
+                    const uint32_t* len, uint32_t n_seq);
+
+/* ---- the hot path ----------------------------------------------------------------------- */
+/* All segments of a batch, host buffers in / host buffers out; == predict() per segment. */
+int trpa_predict_batch(trpa_ctx* ctx, const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands,
+                       uint32_t n_cands, trpa_result* out);
+/* Same, split so that a caller can keep a batch resident in HBM (benchmarking, pipelining). */
+int trpa_batch_upload(trpa_ctx* ctx, const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands,
+                      uint32_t n_cands);
+int trpa_batch_run(trpa_ctx* ctx);
+int trpa_batch_download(trpa_ctx* ctx, trpa_result* out);
+
+/* ---- lower-level entry points (unit tests, micro-benchmarks) ------------------------------ */
+/* edit distance of n_pairs pairs over a private ASCII sequence table; == getAlignmentDNA distance
+ * (hh:133-171).  repeat > 1 re-runs the kernels for timing; kernel_ms (nullable) = device ms/run. */
+int trpa_edit_distance_batch(trpa_ctx* ctx, const char* chars, const uint64_t* off, const uint32_t* len,
+                             uint32_t n_seq, const uint32_t* pair_a, const uint32_t* pair_b, uint32_t n_pairs,
+                             int32_t* out_dist, int repeat, double* kernel_ms);
+/* BLOSUM62 linear-gap global alignment; out3[3*i..] = {mutual score, self score, traced length};
+ * == getAlignmentProtein (hh:173-242); a = horizontal (row 0), b = vertical (row 1). */
+int trpa_protein_align_batch(trpa_ctx* ctx, const char* chars, const uint64_t* off, const uint32_t* len,
+                             uint32_t n_seq, const uint32_t* pair_a, const uint32_t* pair_b, uint32_t n_pairs,
+                             int32_t* out3, int repeat, double* kernel_ms);
+/* Fetch candidate reference segments exactly as getSequence(id,start,stop,left_ext,right_ext)
+ * (hh:856-880) from the loaded reference store; out_chars receives ordinals (0..4 / 0..26),
+ * out_off[i] the start of segment i in out_chars, out_len[i] its length. */
+int trpa_fetch_segments(trpa_ctx* ctx, const uint32_t* ref_seq, const uint32_t* start, const uint32_t* stop,
+                        const uint32_t* left_ext, const uint32_t* right_ext, uint32_t n, uint8_t* out_codes,
+                        uint64_t out_capacity, uint64_t* out_off, uint32_t* out_len);
+/* LCA of node pairs over the loaded taxonomy; == TaxonomyInterface::getLCA. */
+int trpa_lca_batch(trpa_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t n, uint32_t* out);
+/* INT32 ALU-pipe probe: sustained LOP3+IADD3 lane-ops per second on this GPU (roofline denominator). */
+int trpa_int_alu_peak(trpa_ctx* ctx, double* lane_ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAXATOR_RPA_B200_H_ */

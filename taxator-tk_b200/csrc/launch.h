@@ -1,0 +1,34 @@
+// Host-side launch entry points of the CUDA translation units.
+#pragma once
+#include "common.cuh"
+
+namespace trpa {
+
+// edit distance: pairs[0..count) all of one shape (shapes.h); scratch only for multi-strip pairs
+cudaError_t launch_myers(int shape, const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint2* planes,
+                         const u32* nplane, int* out, u32* scratch, u32 scratch_stride, cudaStream_t stream);
+
+// BLOSUM62 linear-gap NW with traced length; out2[pair.out] = {mutual, #diagonal steps}
+// scratch: scratch_stride int2 per pair, needed only when a pair's A is longer than 512 residues
+cudaError_t launch_protein(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,
+                           int2* out2, int2* scratch, u32 scratch_stride, cudaStream_t stream);
+
+// ASCII -> packed stores
+cudaError_t launch_pack_nt(const uint8_t* chars, const u64* off, const SeqDesc* seqs, u32 n_seq, u64 total_words,
+                           uint2* planes, u32* nplane, u32* seq_flags, cudaStream_t stream);
+
+cudaError_t ensure_blosum_constant(int device);
+cudaError_t launch_aa_codes(const uint8_t* chars, uint8_t* out, u64 n, cudaStream_t stream);
+cudaError_t launch_pack_aa(const uint8_t* chars, const u64* off, const u64* woff, const u32* len, u32 n_seq,
+                           u64 total_words, u32* packed, cudaStream_t stream);
+cudaError_t launch_stage_nt(const StageReq* reqs, u32 n_req, const uint2* q_planes, const u32* q_n, const u64* q_woff,
+                            const uint2* r_planes, const u32* r_n, const u64* r_woff, SeqDesc* descs,
+                            uint2* out_planes, u32* out_n, cudaStream_t stream);
+cudaError_t launch_stage_aa(const StageReq* reqs, u32 n_req, const u32* q_packed, const u64* q_woff,
+                            const u32* r_packed, const u64* r_woff, SeqDesc* descs, uint8_t* out, cudaStream_t stream);
+cudaError_t launch_selfscore(SeqDesc* descs, u32 n, const uint8_t* residues, cudaStream_t stream);
+cudaError_t launch_unstage_nt(const SeqDesc* descs, u32 n, const uint2* planes, const u32* nplane,
+                              const u64* out_off, uint8_t* out, cudaStream_t stream);
+cudaError_t launch_alu_probe(u32* sink, int iters, cudaStream_t stream, int* blocks, int* threads);
+
+}  // namespace trpa

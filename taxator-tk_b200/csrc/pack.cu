@@ -1,0 +1,281 @@
+// Sequence store packing and segment staging kernels (HBM-bound byte/bit work).
+//
+// Store layout in HBM (replaces RandomInmemorySeqStoreRO / RandomIndexedSeqstoreRO,
+// core/src/sequencestorage.hh:56-140,318-457):
+//   NT: every sequence starts on a 32-base word boundary; word k of a sequence holds bases
+//       32k..32k+31 as two bit-planes (uint2: .x low bit, .y high bit of A=0,C=1,G=2,T=3) plus an
+//       "is N" plane.  char -> Dna5 as SeqAn does it: A,C,G,T,U (either case) -> 0..3, else N.
+//   AA: 5-bit SeqAn AminoAcid ordinals, 6 per 32-bit word, every sequence word aligned.
+// Staged segments (what the alignment kernels read) use the same NT plane layout / one byte per
+// residue for AA, cut out per getSequence(id,start,stop,left_ext,right_ext) semantics
+// (core/src/taxonpredictionmodelsequence.hh:856-880): clip to the sequence, reverse-complement
+// when rstart > rstop (nucleotide only).
+#include "common.cuh"
+#include "launch.h"
+#include "blosum62_table.h"
+
+namespace trpa {
+
+__constant__ signed char c_blosum[27][32];
+static bool g_blosum_loaded[16] = {false};
+
+cudaError_t ensure_blosum_constant(int device) {
+  if (device >= 0 && device < 16 && g_blosum_loaded[device]) return cudaSuccess;
+  cudaError_t e = cudaMemcpyToSymbol(c_blosum, TRPA_BLOSUM62, sizeof(TRPA_BLOSUM62));
+  if (e == cudaSuccess && device >= 0 && device < 16) g_blosum_loaded[device] = true;
+  return e;
+}
+
+__device__ __forceinline__ u32 dna5_code(u32 c) {
+  c &= 0xdfu;  // fold case (also maps some punctuation onto letters' slots, excluded below)
+  // only true letters reach a match: 'A'..'Z' are 0x41..0x5a in both cases after folding
+  u32 code = 4;
+  if (c == 'A') code = 0;
+  else if (c == 'C') code = 1;
+  else if (c == 'G') code = 2;
+  else if (c == 'T' || c == 'U') code = 3;
+  return code;
+}
+
+__device__ __forceinline__ u32 aa_code(u32 c) {
+  // SeqAn order: A B C D E F G H I J K L M N O P Q R S T U V W Y Z X *   (X=25, '*'=26)
+  if (c >= 'a' && c <= 'z') c -= 32;
+  if (c == '*') return 26;
+  if (c < 'A' || c > 'Z') return 25;
+  if (c <= 'W') return c - 'A';
+  if (c == 'X') return 25;
+  return c - 'A' - 1;  // Y -> 23, Z -> 24
+}
+
+// one warp per output word
+__global__ void pack_nt_kernel(const uint8_t* __restrict__ chars, const u64* __restrict__ off,
+                               const SeqDesc* __restrict__ seqs, u32 n_seq, u64 total_words,
+                               uint2* __restrict__ planes, u32* __restrict__ nplane, u32* __restrict__ seq_flags) {
+  const u32 lane = threadIdx.x & 31;
+  const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
+  for (u64 gw = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; gw < total_words; gw += warps) {
+    // sequence containing word gw: last s with seqs[s].woff <= gw
+    u32 lo = 0, hi = n_seq;
+    while (hi - lo > 1) {
+      u32 mid = (lo + hi) >> 1;
+      if ((u64)seqs[mid].woff <= gw) lo = mid; else hi = mid;
+    }
+    const SeqDesc sd = seqs[lo];
+    const u64 base = (gw - sd.woff) * 32 + lane;
+    u32 code = 0;
+    bool valid = base < sd.len;
+    if (valid) code = dna5_code(chars[off[lo] + base]);
+    const u32 isn = valid && code == 4;
+    const u32 b0 = __ballot_sync(0xffffffffu, valid && !isn && (code & 1));
+    const u32 b1 = __ballot_sync(0xffffffffu, valid && !isn && (code & 2));
+    const u32 bn = __ballot_sync(0xffffffffu, isn);
+    if (lane == 0) {
+      planes[gw] = make_uint2(b0, b1);
+      nplane[gw] = bn;
+      if (bn && seq_flags) atomicOr(&seq_flags[lo], 1u);
+    }
+  }
+}
+
+cudaError_t launch_pack_nt(const uint8_t* chars, const u64* off, const SeqDesc* seqs, u32 n_seq, u64 total_words,
+                           uint2* planes, u32* nplane, u32* seq_flags, cudaStream_t stream) {
+  if (total_words == 0) return cudaSuccess;
+  u64 blocks = (total_words + 7) / 8;  // 8 warps per CTA
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  pack_nt_kernel<<<(u32)blocks, 256, 0, stream>>>(chars, off, seqs, n_seq, total_words, planes, nplane, seq_flags);
+  return cudaGetLastError();
+}
+
+// ASCII -> one ordinal byte per residue at the same offsets
+__global__ void aa_codes_kernel(const uint8_t* __restrict__ chars, uint8_t* __restrict__ out, u64 n) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (uint8_t)aa_code(chars[i]);
+}
+
+cudaError_t launch_aa_codes(const uint8_t* chars, uint8_t* out, u64 n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  u64 blocks = (n + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  aa_codes_kernel<<<(u32)blocks, 256, 0, stream>>>(chars, out, n);
+  return cudaGetLastError();
+}
+
+// 5-bit packing of an ordinal byte stream: word w of sequence s holds residues 6w..6w+5
+__global__ void pack_aa_kernel(const uint8_t* __restrict__ chars, const u64* __restrict__ off,
+                               const u64* __restrict__ woff, const u32* __restrict__ len, u32 n_seq,
+                               u64 total_words, u32* __restrict__ packed) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 gw = (u64)blockIdx.x * blockDim.x + threadIdx.x; gw < total_words; gw += stride) {
+    u32 lo = 0, hi = n_seq;
+    while (hi - lo > 1) {
+      u32 mid = (lo + hi) >> 1;
+      if (woff[mid] <= gw) lo = mid; else hi = mid;
+    }
+    const u64 r0 = (gw - woff[lo]) * 6;
+    u32 w = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (r0 + k < len[lo]) w |= aa_code(chars[off[lo] + r0 + k]) << (5 * k);
+    packed[gw] = w;
+  }
+}
+
+cudaError_t launch_pack_aa(const uint8_t* chars, const u64* off, const u64* woff, const u32* len, u32 n_seq,
+                           u64 total_words, u32* packed, cudaStream_t stream) {
+  if (total_words == 0) return cudaSuccess;
+  u64 blocks = (total_words + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  pack_aa_kernel<<<(u32)blocks, 256, 0, stream>>>(chars, off, woff, len, n_seq, total_words, packed);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ staging
+// 32 consecutive bits of a plane starting at (possibly negative) bit position s relative to word
+// pointer p; bits below 0 read as 0.  The store arrays carry one pad word at the end.
+__device__ __forceinline__ u32 window_x(const uint2* p, long long s) {
+  if (s < 0) { const u32 sh = (u32)(-s); return sh >= 32 ? 0u : (p[0].x << sh); }
+  const u64 w = (u64)s >> 5; const u32 sh = (u32)s & 31;
+  return sh ? __funnelshift_r(p[w].x, p[w + 1].x, sh) : p[w].x;
+}
+__device__ __forceinline__ u32 window_y(const uint2* p, long long s) {
+  if (s < 0) { const u32 sh = (u32)(-s); return sh >= 32 ? 0u : (p[0].y << sh); }
+  const u64 w = (u64)s >> 5; const u32 sh = (u32)s & 31;
+  return sh ? __funnelshift_r(p[w].y, p[w + 1].y, sh) : p[w].y;
+}
+__device__ __forceinline__ u32 window_n(const u32* p, long long s) {
+  if (s < 0) { const u32 sh = (u32)(-s); return sh >= 32 ? 0u : (p[0] << sh); }
+  const u64 w = (u64)s >> 5; const u32 sh = (u32)s & 31;
+  return sh ? __funnelshift_r(p[w], p[w + 1], sh) : p[w];
+}
+
+// one warp per request
+__global__ void stage_nt_kernel(const StageReq* __restrict__ reqs, u32 n_req,
+                                const uint2* __restrict__ q_planes, const u32* __restrict__ q_n, const u64* __restrict__ q_woff,
+                                const uint2* __restrict__ r_planes, const u32* __restrict__ r_n, const u64* __restrict__ r_woff,
+                                SeqDesc* __restrict__ descs, uint2* __restrict__ out_planes, u32* __restrict__ out_n) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_req; r += warps) {
+    const StageReq rq = reqs[r];
+    const SeqDesc d = descs[rq.desc];
+    const uint2* sp = rq.store ? r_planes + r_woff[rq.seq] : q_planes + q_woff[rq.seq];
+    const u32* sn = rq.store ? r_n + r_woff[rq.seq] : q_n + q_woff[rq.seq];
+    const u32 nwords = (d.len + 31) >> 5;
+    u32 anyn = 0;
+    for (u32 k = lane; k < nwords; k += 32) {
+      const u32 rem = d.len - 32 * k;
+      const u32 valid = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+      u32 p0, p1, pn;
+      if (!rq.rev) {
+        const long long s = (long long)rq.begin + 32ll * k;
+        p0 = window_x(sp, s); p1 = window_y(sp, s); pn = window_n(sn, s);
+      } else {
+        // out base j = complement(src[begin + len - 1 - j])
+        const long long s = (long long)rq.begin + (long long)d.len - 32ll * k - 32ll;
+        p0 = ~__brev(window_x(sp, s)); p1 = ~__brev(window_y(sp, s)); pn = __brev(window_n(sn, s));
+      }
+      pn &= valid;
+      p0 &= valid & ~pn; p1 &= valid & ~pn;
+      out_planes[(u64)d.woff + k] = make_uint2(p0, p1);
+      out_n[(u64)d.woff + k] = pn;
+      anyn |= pn;
+    }
+    anyn = __reduce_or_sync(0xffffffffu, anyn);
+    if (lane == 0) descs[rq.desc].flags = anyn ? 1u : 0u;
+  }
+}
+
+cudaError_t launch_stage_nt(const StageReq* reqs, u32 n_req, const uint2* q_planes, const u32* q_n, const u64* q_woff,
+                            const uint2* r_planes, const u32* r_n, const u64* r_woff, SeqDesc* descs,
+                            uint2* out_planes, u32* out_n, cudaStream_t stream) {
+  if (n_req == 0) return cudaSuccess;
+  u32 blocks = (n_req + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  stage_nt_kernel<<<blocks, 256, 0, stream>>>(reqs, n_req, q_planes, q_n, q_woff, r_planes, r_n, r_woff, descs,
+                                              out_planes, out_n);
+  return cudaGetLastError();
+}
+
+// AA staging: unpack 5-bit residues to bytes; SeqDesc.pad receives the self score
+// sum_i BLOSUM62(a_i,a_i) (== NW(X,X), hh:190-191; equality pinned in tests).  One warp per request.
+__global__ void stage_aa_kernel(const StageReq* __restrict__ reqs, u32 n_req, const u32* __restrict__ q_packed,
+                                const u64* __restrict__ q_woff, const u32* __restrict__ r_packed,
+                                const u64* __restrict__ r_woff, SeqDesc* __restrict__ descs,
+                                uint8_t* __restrict__ out) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_req; r += warps) {
+    const StageReq rq = reqs[r];
+    const SeqDesc d = descs[rq.desc];
+    const u32* sp = rq.store ? r_packed + r_woff[rq.seq] : q_packed + q_woff[rq.seq];
+    int self = 0;
+    for (u32 k = lane; k < d.len; k += 32) {
+      const u32 idx = rq.begin + k;
+      const u32 code = (sp[idx / 6] >> (5 * (idx % 6))) & 31u;
+      out[(u64)d.woff + k] = (uint8_t)code;
+      self += c_blosum[code][code];
+    }
+    self = __reduce_add_sync(0xffffffffu, self);
+    if (lane == 0) { descs[rq.desc].pad = (u32)self; descs[rq.desc].flags = 0; }
+  }
+}
+
+cudaError_t launch_stage_aa(const StageReq* reqs, u32 n_req, const u32* q_packed, const u64* q_woff,
+                            const u32* r_packed, const u64* r_woff, SeqDesc* descs, uint8_t* out, cudaStream_t stream) {
+  if (n_req == 0) return cudaSuccess;
+  u32 blocks = (n_req + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  stage_aa_kernel<<<blocks, 256, 0, stream>>>(reqs, n_req, q_packed, q_woff, r_packed, r_woff, descs, out);
+  return cudaGetLastError();
+}
+
+// self scores for a table of byte sequences (low-level API); one warp per sequence
+__global__ void selfscore_kernel(SeqDesc* __restrict__ descs, u32 n, const uint8_t* __restrict__ residues) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
+    const SeqDesc d = descs[s];
+    int self = 0;
+    for (u32 k = lane; k < d.len; k += 32) { const u32 c = residues[(u64)d.woff + k]; self += c_blosum[c][c]; }
+    self = __reduce_add_sync(0xffffffffu, self);
+    if (lane == 0) descs[s].pad = (u32)self;
+  }
+}
+
+cudaError_t launch_selfscore(SeqDesc* descs, u32 n, const uint8_t* residues, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  u32 blocks = (n + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  selfscore_kernel<<<blocks, 256, 0, stream>>>(descs, n, residues);
+  return cudaGetLastError();
+}
+
+// staged NT planes -> ordinal bytes (only for trpa_fetch_segments, the byte-for-byte fetch test)
+__global__ void unstage_nt_kernel(const SeqDesc* __restrict__ descs, u32 n, const uint2* __restrict__ planes,
+                                  const u32* __restrict__ nplane, const u64* __restrict__ out_off,
+                                  uint8_t* __restrict__ out) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
+    const SeqDesc d = descs[s];
+    for (u32 j = lane; j < d.len; j += 32) {
+      const uint2 p = planes[(u64)d.woff + (j >> 5)];
+      const u32 nn = nplane[(u64)d.woff + (j >> 5)];
+      const u32 b = j & 31;
+      u32 code = ((p.x >> b) & 1u) | (((p.y >> b) & 1u) << 1);
+      if ((nn >> b) & 1u) code = 4;
+      out[out_off[s] + j] = (uint8_t)code;
+    }
+  }
+}
+
+cudaError_t launch_unstage_nt(const SeqDesc* descs, u32 n, const uint2* planes, const u32* nplane,
+                              const u64* out_off, uint8_t* out, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  u32 blocks = (n + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  unstage_nt_kernel<<<blocks, 256, 0, stream>>>(descs, n, planes, nplane, out_off, out);
+  return cudaGetLastError();
+}
+
+}  // namespace trpa

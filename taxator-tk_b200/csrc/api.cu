@@ -1,0 +1,804 @@
+// C ABI of the B200-native RPA hot path (include/taxator_rpa_b200.h) + the per-round driver:
+//   decide kernel (one thread per query segment, machine.h) -> stage kernel (pack.cu)
+//   -> shape bucketing -> edit-distance / protein kernels (myers.cuh / protein.cu) -> decide ...
+// There is no CPU fallback: every compute entry point needs a CUDA device.
+// Compile with --fmad=false (decision arithmetic must match the reference's IEEE float/double ops).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "launch.h"
+#include "machine.h"
+#include "hostprep.h"
+
+namespace trpa {
+
+static thread_local std::string g_error;
+void set_error(const std::string& s) { g_error = s; }
+int alu_probe_ops_per_iter();
+
+#define CK(expr)                                                                        \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      set_error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + " " + #expr + ": " + cudaGetErrorString(_e)); \
+      return TRPA_ERR_CUDA;                                                             \
+    }                                                                                   \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  int ensure(size_t n) {
+    if (n <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 16;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e != cudaSuccess) { set_error(std::string("cudaMalloc ") + std::to_string(want * sizeof(T)) + " B: " + cudaGetErrorString(e)); cudaGetLastError(); return TRPA_ERR_NOMEM; }
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Store {
+  int alphabet = -1;
+  u32 n_seq = 0;
+  u64 n_words = 0;
+  DevBuf<uint2> planes;
+  DevBuf<u32> nplane;
+  DevBuf<u32> packed;  // AA
+  DevBuf<u64> woff;
+  DevBuf<u32> len;
+  u32 max_len = 0;
+  void release() { planes.release(); nplane.release(); packed.release(); woff.release(); len.release(); n_seq = 0; alphabet = -1; }
+};
+
+struct EventPair { cudaEvent_t a, b; int kind; };
+
+}  // namespace trpa
+
+using namespace trpa;
+
+struct trpa_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  float exclude_factor = 0.5f, toppercent = 0.05f;
+  u64 arena_bytes = 0;
+  // taxonomy
+  DevBuf<u32> t_parent, t_left, t_right;
+  DevBuf<uint8_t> t_depth;
+  u32 n_nodes = 0, root = 0;
+  Store store[2];
+  // batch (whole batch resident)
+  std::vector<trpa_segment> h_segs;
+  std::vector<trpa_candidate> h_cands;
+  std::vector<u32> chunk_begin;  // segment index boundaries
+  u32 n_segs = 0, n_cands = 0;
+  u32 max_stage_len = 0;
+  bool batch_ready = false;
+  DevBuf<trpa_segment> d_segs;
+  DevBuf<trpa_candidate> d_cands;
+  DevBuf<trpa_result> d_results;
+  DevBuf<SegState> d_state;
+  DevBuf<float> d_qd, d_qsim, d_bf_d;
+  DevBuf<uint8_t> d_cflags;
+  DevBuf<u32> d_og_i, d_bf_node;
+  DevBuf<int32_t> d_og_d;
+  DevBuf<int32_t> d_res;      // NT: 1 int per slot; AA: 2 ints per slot
+  DevBuf<SeqDesc> d_descs;
+  DevBuf<PairDesc> d_pairs, d_pairs_sorted;
+  DevBuf<StageReq> d_stage;
+  DevBuf<u32> d_counters;
+  DevBuf<u32> d_hist;         // kNumShapes counts + kNumShapes cursors
+  DevBuf<uint2> d_buckets;    // kNumShapes {start,count}
+  DevBuf<uint2> arena_planes;
+  DevBuf<u32> arena_n;
+  DevBuf<uint8_t> arena_aa;
+  u64 arena_units = 0;
+  DevBuf<u32> scratch;
+  DevBuf<int2> scratch_aa;
+  u32* h_counters = nullptr;  // pinned
+  // profiling
+  trpa_profile prof;
+  std::vector<EventPair> ev_pool;
+  size_t ev_used = 0;
+};
+
+namespace trpa {
+
+// ------------------------------------------------------------------------------------ kernels
+__global__ void decide_kernel(Batch B, u32 seg_begin, u32 seg_end) {
+  const u32 s = seg_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= seg_end) return;
+  if (B.st[s].phase == PH_DONE) return;
+  Machine M(B, s);
+  M.advance();
+  if (B.st[s].phase != PH_DONE) atomicAdd(&B.counters[CN_ACTIVE], 1u);
+}
+
+__global__ void init_state_kernel(SegState* st, u32 n) {
+  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) st[s].phase = PH_INIT;
+}
+
+// exact shape of every pair of the round (needs the staged N flags) + histogram
+__global__ void classify_kernel(PairDesc* pairs, const u32* counters, const SeqDesc* descs, u32* hist) {
+  const u32 n = counters[CN_PAIRS];
+  for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    PairDesc p = pairs[k];
+    const SeqDesc a = descs[p.a], b = descs[p.b];
+    const u32 m = a.len < b.len ? a.len : b.len;
+    const int shape = choose_shape((m + 31u) >> 5, (a.flags | b.flags) & 1u);
+    pairs[k].pad = (u32)shape;
+    atomicAdd(&hist[shape], 1u);
+  }
+}
+__global__ void scan_kernel(u32* hist, uint2* buckets) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    u32 acc = 0;
+    for (int s = 0; s < kNumShapes; ++s) {
+      const u32 c = hist[s];
+      buckets[s] = make_uint2(acc, c);
+      hist[kNumShapes + s] = acc;  // scatter cursor
+      acc += c;
+    }
+  }
+}
+__global__ void scatter_kernel(const PairDesc* pairs, const u32* counters, u32* hist, PairDesc* sorted) {
+  const u32 n = counters[CN_PAIRS];
+  for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const PairDesc p = pairs[k];
+    const u32 pos = atomicAdd(&hist[kNumShapes + p.pad], 1u);
+    sorted[pos] = p;
+  }
+}
+
+__global__ void lca_kernel(Taxonomy T, const u32* a, const u32* b, u32 n, u32* out) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = tx_lca(T, a[i], b[i]);
+}
+
+// ------------------------------------------------------------------------------------ helpers
+static int begin_event(trpa_ctx* c, int kind) {
+  if (c->ev_used == c->ev_pool.size()) {
+    EventPair e; e.kind = kind;
+    if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return -1;
+    c->ev_pool.push_back(e);
+  }
+  c->ev_pool[c->ev_used].kind = kind;
+  cudaEventRecord(c->ev_pool[c->ev_used].a, c->stream);
+  return (int)c->ev_used++;
+}
+static void end_event(trpa_ctx* c, int id) {
+  if (id >= 0) cudaEventRecord(c->ev_pool[id].b, c->stream);
+}
+enum { EV_MYERS = 0, EV_PROTEIN, EV_STAGE, EV_DECIDE, EV_OTHER };
+// call after a stream sync
+static void harvest_events(trpa_ctx* c) {
+  for (size_t i = 0; i < c->ev_used; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev_pool[i].a, c->ev_pool[i].b) != cudaSuccess) { cudaGetLastError(); continue; }
+    switch (c->ev_pool[i].kind) {
+      case EV_MYERS: c->prof.ms_edit_distance += ms; break;
+      case EV_PROTEIN: c->prof.ms_protein += ms; break;
+      case EV_STAGE: c->prof.ms_stage += ms; break;
+      case EV_DECIDE: c->prof.ms_decide += ms; break;
+      default: c->prof.ms_other += ms; break;
+    }
+  }
+  c->ev_used = 0;
+}
+
+static int use_device(trpa_ctx* c) {
+  CK(cudaSetDevice(c->device));
+  return 0;
+}
+
+static Taxonomy dev_tax(trpa_ctx* c) { return Taxonomy{c->t_parent.p, c->t_left.p, c->t_right.p, c->t_depth.p, c->root}; }
+
+// Shared by the pipeline and the low-level API: run the edit-distance kernels over `n_pairs` pairs
+// whose exact shapes have already been bucketed on the device (d_buckets), given host-side upper
+// bounds per geometry.
+static int launch_myers_buckets(trpa_ctx* c, const u32* geom_counts, const PairDesc* sorted, const SeqDesc* descs,
+                                const uint2* planes, const u32* nplane, int* out, u32 max_len) {
+  const u32 stride = (max_len + 31) / 32 + 1;
+  for (int g = 0; g < kNumW * kNumL; ++g) {
+    const u32 cnt = geom_counts[g];
+    if (!cnt) continue;
+    const int L = 1 << shape_lidx(g);
+    const int W = shape_W(shape_widx(g));
+    u32* scr = nullptr;
+    if (L == 32 && (u64)stride * 32 > (u64)32 * W * 32) {  // some pattern may need >1 strip
+      if (c->scratch.ensure((size_t)cnt * 3 * stride)) return TRPA_ERR_NOMEM;
+      scr = c->scratch.p;
+    }
+    for (int hasn = 0; hasn < 2; ++hasn) {
+      const int shape = g + hasn * kNumW * kNumL;
+      CK(launch_myers(shape, sorted, cnt, descs, planes, nplane, out, scr, stride, c->d_buckets.p + shape, c->stream));
+      c->prof.launches_edit_distance++;
+    }
+  }
+  return 0;
+}
+
+}  // namespace trpa
+
+// =========================================================================================== ABI
+extern "C" {
+
+int trpa_abi_version(void) { return TRPA_ABI_VERSION; }
+const char* trpa_last_error(void) { return g_error.c_str(); }
+
+trpa_ctx* trpa_create(int device, void* cuda_stream) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)");
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) { set_error("bad device index"); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
+  trpa_ctx* c = new trpa_ctx();
+  c->device = device;
+  memset(&c->prof, 0, sizeof(c->prof));
+  if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
+  else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete c; return nullptr; }
+    c->own_stream = true;
+  }
+  if (cudaMallocHost(&c->h_counters, sizeof(u32) * (kNumCounters + 2 * kNumShapes)) != cudaSuccess) { set_error("cudaMallocHost failed"); delete c; return nullptr; }
+  return c;
+}
+
+void trpa_destroy(trpa_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->t_parent.release(); c->t_left.release(); c->t_right.release(); c->t_depth.release();
+  c->store[0].release(); c->store[1].release();
+  c->d_segs.release(); c->d_cands.release(); c->d_results.release(); c->d_state.release();
+  c->d_qd.release(); c->d_qsim.release(); c->d_bf_d.release(); c->d_cflags.release(); c->d_og_i.release();
+  c->d_bf_node.release(); c->d_og_d.release(); c->d_res.release(); c->d_descs.release(); c->d_pairs.release();
+  c->d_pairs_sorted.release(); c->d_stage.release(); c->d_counters.release(); c->d_hist.release();
+  c->d_buckets.release(); c->arena_planes.release(); c->arena_n.release(); c->arena_aa.release();
+  c->scratch.release(); c->scratch_aa.release();
+  for (auto& e : c->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  if (c->h_counters) cudaFreeHost(c->h_counters);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int trpa_set_params(trpa_ctx* c, float exclude_factor, float toppercent) {
+  if (!c) { set_error("null ctx"); return TRPA_ERR_ARG; }
+  c->exclude_factor = exclude_factor; c->toppercent = toppercent;
+  return 0;
+}
+int trpa_set_arena_bytes(trpa_ctx* c, uint64_t bytes) {
+  if (!c) { set_error("null ctx"); return TRPA_ERR_ARG; }
+  c->arena_bytes = bytes;
+  return 0;
+}
+int trpa_profile_reset(trpa_ctx* c) { if (!c) return TRPA_ERR_ARG; memset(&c->prof, 0, sizeof(c->prof)); return 0; }
+int trpa_profile_get(trpa_ctx* c, trpa_profile* out) { if (!c || !out) return TRPA_ERR_ARG; *out = c->prof; return 0; }
+
+int trpa_load_taxonomy(trpa_ctx* c, const uint32_t* parent, const uint32_t* left, const uint32_t* right,
+                       const uint8_t* depth, uint32_t n_nodes, uint32_t root) {
+  if (!c || !parent || !left || !right || !depth || n_nodes == 0 || root >= n_nodes) { set_error("bad taxonomy arguments"); return TRPA_ERR_ARG; }
+  for (u32 i = 0; i < n_nodes; ++i) {
+    if (parent[i] >= n_nodes) { set_error("taxonomy: parent index out of range"); return TRPA_ERR_ARG; }
+    if (depth[i] >= 64) { set_error("taxonomy: depth >= 64 not supported"); return TRPA_ERR_ARG; }
+  }
+  if (parent[root] != root) { set_error("taxonomy: parent[root] must be root"); return TRPA_ERR_ARG; }
+  if (use_device(c)) return TRPA_ERR_CUDA;
+  if (c->t_parent.ensure(n_nodes) || c->t_left.ensure(n_nodes) || c->t_right.ensure(n_nodes) || c->t_depth.ensure(n_nodes)) return TRPA_ERR_NOMEM;
+  CK(cudaMemcpyAsync(c->t_parent.p, parent, 4ull * n_nodes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->t_left.p, left, 4ull * n_nodes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->t_right.p, right, 4ull * n_nodes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->t_depth.p, depth, 1ull * n_nodes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->n_nodes = n_nodes; c->root = root;
+  return 0;
+}
+
+int trpa_load_store(trpa_ctx* c, int store, int alphabet, const char* chars, const uint64_t* off, const uint32_t* len,
+                    uint32_t n_seq) {
+  if (!c || store < 0 || store > 1 || (alphabet != TRPA_ALPHA_NT && alphabet != TRPA_ALPHA_AA) || (n_seq && (!chars || !off || !len))) {
+    set_error("bad store arguments"); return TRPA_ERR_ARG;
+  }
+  if (use_device(c)) return TRPA_ERR_CUDA;
+  Store& S = c->store[store];
+  S.release();
+  std::vector<u64> woff(n_seq + 1);
+  u64 words = 0, nchars = 0; u32 maxlen = 0;
+  const u32 per = alphabet == TRPA_ALPHA_NT ? 32 : 6;
+  for (u32 i = 0; i < n_seq; ++i) {
+    woff[i] = words;
+    words += ((u64)len[i] + per - 1) / per;
+    nchars = std::max<u64>(nchars, off[i] + len[i]);
+    maxlen = std::max(maxlen, len[i]);
+  }
+  woff[n_seq] = words;
+  if (alphabet == TRPA_ALPHA_NT && words >= 0xffffffffull) {
+    // SeqDesc.woff of the packing descriptor is 32 bit; stores beyond 137 Gbases need a wider layout
+    set_error("nucleotide store larger than 2^32 words is not supported yet"); return TRPA_ERR_ARG;
+  }
+  DevBuf<uint8_t> d_chars; DevBuf<u64> d_off;
+  if (d_chars.ensure(nchars + 1) || d_off.ensure(n_seq + 1) || S.woff.ensure(n_seq + 1) || S.len.ensure(n_seq + 1)) return TRPA_ERR_NOMEM;
+  CK(cudaMemcpyAsync(d_chars.p, chars, nchars, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_off.p, off, 8ull * n_seq, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(S.woff.p, woff.data(), 8ull * (n_seq + 1), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(S.len.p, len, 4ull * n_seq, cudaMemcpyHostToDevice, c->stream));
+  if (alphabet == TRPA_ALPHA_NT) {
+    std::vector<SeqDesc> sd(n_seq);
+    for (u32 i = 0; i < n_seq; ++i) sd[i] = SeqDesc{(u32)woff[i], len[i], 0, 0};
+    DevBuf<SeqDesc> d_sd;
+    if (d_sd.ensure(n_seq + 1) || S.planes.ensure(words + 2) || S.nplane.ensure(words + 2)) return TRPA_ERR_NOMEM;
+    CK(cudaMemsetAsync(S.planes.p, 0, (words + 2) * sizeof(uint2), c->stream));
+    CK(cudaMemsetAsync(S.nplane.p, 0, (words + 2) * sizeof(u32), c->stream));
+    CK(cudaMemcpyAsync(d_sd.p, sd.data(), sizeof(SeqDesc) * n_seq, cudaMemcpyHostToDevice, c->stream));
+    CK(launch_pack_nt(d_chars.p, d_off.p, d_sd.p, n_seq, words, S.planes.p, S.nplane.p, nullptr, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    d_sd.release();
+  } else {
+    if (S.packed.ensure(words + 2)) return TRPA_ERR_NOMEM;
+    CK(cudaMemsetAsync(S.packed.p, 0, (words + 2) * sizeof(u32), c->stream));
+    CK(launch_pack_aa(d_chars.p, d_off.p, S.woff.p, S.len.p, n_seq, words, S.packed.p, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  d_chars.release(); d_off.release();
+  S.alphabet = alphabet; S.n_seq = n_seq; S.n_words = words; S.max_len = maxlen;
+  c->batch_ready = false;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ the hot path
+int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands,
+                      uint32_t n_cands) {
+  if (!c || (n_segs && !segs) || (n_cands && !cands)) { set_error("bad batch arguments"); return TRPA_ERR_ARG; }
+  if (use_device(c)) return TRPA_ERR_CUDA;
+  if (c->n_nodes == 0) { set_error("taxonomy not loaded"); return TRPA_ERR_STATE; }
+  const Store& Q = c->store[TRPA_STORE_QUERY];
+  const Store& R = c->store[TRPA_STORE_REF];
+  if (Q.alphabet < 0 || R.alphabet < 0 || Q.alphabet != R.alphabet) { set_error("query/reference stores not loaded or of different alphabets"); return TRPA_ERR_STATE; }
+  if ((u64)n_segs + n_cands >= 0xfffffff0ull) { set_error("batch too large"); return TRPA_ERR_ARG; }
+  const bool protein = Q.alphabet == TRPA_ALPHA_AA;
+  // validate (the reference throws SequenceNotFound / TaxonNotFound at parse time)
+  for (u32 s = 0; s < n_segs; ++s) {
+    if ((u64)segs[s].cand_begin + segs[s].cand_count > n_cands) { set_error("segment candidate range out of bounds"); return TRPA_ERR_ARG; }
+    if (segs[s].cand_count && segs[s].query_seq >= Q.n_seq) { set_error("segment query ordinal out of range"); return TRPA_ERR_ARG; }
+  }
+  for (u32 k = 0; k < n_cands; ++k) {
+    if (cands[k].ref_seq >= R.n_seq) { set_error("candidate reference ordinal out of range"); return TRPA_ERR_ARG; }
+    if (cands[k].node >= c->n_nodes) { set_error("candidate taxon node out of range"); return TRPA_ERR_ARG; }
+    if (cands[k].qstart > cands[k].qstop || cands[k].qstart == 0) { set_error("candidate query range invalid (qstart must be >= 1 and <= qstop)"); return TRPA_ERR_ARG; }
+    if (cands[k].rstart == 0 || cands[k].rstop == 0) { set_error("candidate reference coordinates are 1-based"); return TRPA_ERR_ARG; }
+  }
+  c->h_segs.assign(segs, segs + n_segs);
+  c->h_cands.assign(cands, cands + n_cands);
+  sort_candidates(c->h_segs.data(), n_segs, c->h_cands.data());
+  c->n_segs = n_segs; c->n_cands = n_cands;
+
+  // arena + chunk plan
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const u64 per_cand = 36 + 4 + 4 + 4 + 1 + 4 + 4 + 4 + 8 + 16 + 32 + 20 + 16;  // rough per-candidate work bytes
+  const u64 fixed = (u64)n_cands * per_cand + (u64)n_segs * (sizeof(SegState) + sizeof(trpa_result) + 96);
+  u64 arena_bytes = c->arena_bytes;
+  if (!arena_bytes) {
+    const u64 avail = free_b > fixed ? free_b - fixed : 0;
+    arena_bytes = avail / 2;
+  }
+  const u64 unit_bytes = protein ? 1 : 12;
+  u64 units_cap = std::min<u64>(arena_bytes / unit_bytes, 0xfffffff0ull);
+  std::vector<u64> bound(n_segs);
+  u64 total_bound = 0, max_bound = 0; u32 max_len = 0;
+  for (u32 s = 0; s < n_segs; ++s) {
+    bound[s] = segment_arena_bound(c->h_segs[s], c->h_cands.data(), protein);
+    total_bound += bound[s];
+    max_bound = std::max(max_bound, bound[s]);
+  }
+  for (u32 k = 0; k < n_cands; ++k) {
+    const trpa_candidate& x = c->h_cands[k];
+    const u64 span = (x.rstart <= x.rstop ? (u64)x.rstop - x.rstart : (u64)x.rstart - x.rstop) + 1;
+    max_len = (u32)std::min<u64>(0xffffffffull, std::max<u64>(max_len, span));
+  }
+  // extensions can add at most the query range; sequences are clipped to the store anyway
+  max_len = std::min<u64>((u64)max_len + Q.max_len, std::max(R.max_len, Q.max_len));
+  c->max_stage_len = max_len;
+  units_cap = std::min(units_cap, std::max<u64>(total_bound, 1));
+  if (max_bound > units_cap) { set_error("staging arena too small for the largest segment; raise trpa_set_arena_bytes"); return TRPA_ERR_NOMEM; }
+  c->chunk_begin.clear();
+  c->chunk_begin.push_back(0);
+  u64 acc = 0;
+  for (u32 s = 0; s < n_segs; ++s) {
+    if (acc + bound[s] > units_cap) { c->chunk_begin.push_back(s); acc = 0; }
+    acc += bound[s];
+  }
+  c->chunk_begin.push_back(n_segs);
+  c->arena_units = units_cap;
+
+  const size_t nslots = (size_t)n_cands + n_segs;
+  if (c->d_segs.ensure(n_segs + 1) || c->d_cands.ensure(n_cands + 1) || c->d_results.ensure(n_segs + 1) ||
+      c->d_state.ensure(n_segs + 1) || c->d_qd.ensure(n_cands + 1) || c->d_qsim.ensure(n_cands + 1) ||
+      c->d_bf_d.ensure(nslots + 1) || c->d_bf_node.ensure(nslots + 1) || c->d_cflags.ensure(n_cands + 1) ||
+      c->d_og_i.ensure(n_cands + 1) || c->d_og_d.ensure(n_cands + 1) || c->d_res.ensure(2 * nslots + 2) ||
+      c->d_descs.ensure(nslots + 1) || c->d_pairs.ensure(nslots + 1) || c->d_pairs_sorted.ensure(nslots + 1) ||
+      c->d_stage.ensure(nslots + 1) || c->d_counters.ensure(kNumCounters) || c->d_hist.ensure(2 * kNumShapes) ||
+      c->d_buckets.ensure(kNumShapes))
+    return TRPA_ERR_NOMEM;
+  if (protein) { if (c->arena_aa.ensure(units_cap + 16)) return TRPA_ERR_NOMEM; }
+  else { if (c->arena_planes.ensure(units_cap + 2) || c->arena_n.ensure(units_cap + 2)) return TRPA_ERR_NOMEM; }
+  CK(cudaMemcpyAsync(c->d_segs.p, c->h_segs.data(), sizeof(trpa_segment) * n_segs, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_cands.p, c->h_cands.data(), sizeof(trpa_candidate) * n_cands, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->batch_ready = true;
+  return 0;
+}
+
+int trpa_batch_run(trpa_ctx* c) {
+  if (!c) { set_error("null ctx"); return TRPA_ERR_ARG; }
+  if (!c->batch_ready) { set_error("no batch uploaded"); return TRPA_ERR_STATE; }
+  if (use_device(c)) return TRPA_ERR_CUDA;
+  const Store& Q = c->store[TRPA_STORE_QUERY];
+  const Store& R = c->store[TRPA_STORE_REF];
+  const bool protein = Q.alphabet == TRPA_ALPHA_AA;
+  const u32 n_segs = c->n_segs, n_cands = c->n_cands;
+  if (n_segs == 0) return 0;
+
+  Batch B;
+  B.segs = c->d_segs.p; B.cands = c->d_cands.p; B.n_segs = n_segs; B.n_cands = n_cands;
+  B.q_len = Q.len.p; B.r_len = R.len.p;
+  B.tax = dev_tax(c);
+  B.protein = protein ? 1 : 0;
+  B.exclude_factor = c->exclude_factor;
+  B.reeval_bandwidth_factor = 1. - c->toppercent;  // taxonpredictionmodelsequence.hh:334
+  B.st = c->d_state.p; B.qd = c->d_qd.p; B.qsim = c->d_qsim.p; B.cflags = c->d_cflags.p;
+  B.og_i = c->d_og_i.p; B.og_d = c->d_og_d.p; B.bf_d = c->d_bf_d.p; B.bf_node = c->d_bf_node.p;
+  B.res_nt = c->d_res.p; B.res_aa = c->d_res.p;
+  B.descs = c->d_descs.p; B.arena_capacity = (u32)c->arena_units;
+  B.pairs = c->d_pairs.p; B.stage = c->d_stage.p; B.counters = c->d_counters.p; B.results = c->d_results.p;
+
+  init_state_kernel<<<(n_segs + 255) / 256, 256, 0, c->stream>>>(c->d_state.p, n_segs);
+  CK(cudaGetLastError());
+  if (protein) CK(ensure_blosum_constant(c->device));
+
+  for (size_t ch = 0; ch + 1 < c->chunk_begin.size(); ++ch) {
+    const u32 sb = c->chunk_begin[ch], se = c->chunk_begin[ch + 1];
+    if (se == sb) continue;
+    CK(cudaMemsetAsync(c->d_counters.p, 0, sizeof(u32) * kNumCounters, c->stream));
+    for (u32 round = 0;; ++round) {
+      int ev = begin_event(c, EV_DECIDE);
+      decide_kernel<<<(se - sb + 63) / 64, 64, 0, c->stream>>>(B, sb, se);
+      CK(cudaGetLastError());
+      end_event(c, ev);
+      c->prof.launches_decide++;
+      CK(cudaMemcpyAsync(c->h_counters, c->d_counters.p, sizeof(u32) * kNumCounters, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      harvest_events(c);
+      const u32 n_pairs = c->h_counters[CN_PAIRS], n_stage = c->h_counters[CN_STAGE], n_active = c->h_counters[CN_ACTIVE];
+      if (c->h_counters[CN_OVERFLOW]) { set_error("internal: staging arena overflow"); return TRPA_ERR_STATE; }
+      if (n_pairs == 0) {
+        if (n_active) { set_error("internal: segments active without pending alignments"); return TRPA_ERR_STATE; }
+        break;
+      }
+      c->prof.rounds++;
+      c->prof.pairs += n_pairs;
+      // --- stage
+      ev = begin_event(c, EV_STAGE);
+      if (protein)
+        CK(launch_stage_aa(c->d_stage.p, n_stage, Q.packed.p, Q.woff.p, R.packed.p, R.woff.p, c->d_descs.p, c->arena_aa.p, c->stream));
+      else
+        CK(launch_stage_nt(c->d_stage.p, n_stage, Q.planes.p, Q.nplane.p, Q.woff.p, R.planes.p, R.nplane.p, R.woff.p,
+                           c->d_descs.p, c->arena_planes.p, c->arena_n.p, c->stream));
+      end_event(c, ev);
+      if (n_stage) c->prof.launches_stage++;
+      // --- align
+      if (protein) {
+        int2* scr = nullptr; u32 stride = 0;
+        if (c->max_stage_len > 512) {
+          stride = c->max_stage_len + 2;
+          if (c->scratch_aa.ensure((size_t)n_pairs * stride)) return TRPA_ERR_NOMEM;
+          scr = c->scratch_aa.p;
+        }
+        ev = begin_event(c, EV_PROTEIN);
+        CK(launch_protein(c->d_pairs.p, n_pairs, c->d_descs.p, c->arena_aa.p, (int2*)c->d_res.p, scr, stride, c->stream));
+        end_event(c, ev);
+        c->prof.launches_protein++;
+      } else {
+        ev = begin_event(c, EV_OTHER);
+        CK(cudaMemsetAsync(c->d_hist.p, 0, sizeof(u32) * 2 * kNumShapes, c->stream));
+        const u32 blocks = std::min<u32>((n_pairs + 255) / 256, 148 * 8);
+        classify_kernel<<<blocks, 256, 0, c->stream>>>(c->d_pairs.p, c->d_counters.p, c->d_descs.p, c->d_hist.p);
+        scan_kernel<<<1, 32, 0, c->stream>>>(c->d_hist.p, c->d_buckets.p);
+        scatter_kernel<<<blocks, 256, 0, c->stream>>>(c->d_pairs.p, c->d_counters.p, c->d_hist.p, c->d_pairs_sorted.p);
+        CK(cudaGetLastError());
+        end_event(c, ev);
+        c->prof.launches_other += 3;
+        ev = begin_event(c, EV_MYERS);
+        int rc = launch_myers_buckets(c, c->h_counters + CN_GEOM0, c->d_pairs_sorted.p, c->d_descs.p, c->arena_planes.p,
+                                      c->arena_n.p, c->d_res.p, c->max_stage_len);
+        if (rc) return rc;
+        end_event(c, ev);
+      }
+      // reset the per-round counters, keep the arena cursor
+      CK(cudaMemsetAsync(c->d_counters.p + CN_PAIRS, 0, sizeof(u32) * 3, c->stream));
+      CK(cudaMemsetAsync(c->d_counters.p + CN_GEOM0, 0, sizeof(u32) * kNumW * kNumL, c->stream));
+    }
+  }
+  // totals for the profile
+  return 0;
+}
+
+int trpa_batch_download(trpa_ctx* c, trpa_result* out) {
+  if (!c || !out) { set_error("bad arguments"); return TRPA_ERR_ARG; }
+  if (!c->batch_ready) { set_error("no batch uploaded"); return TRPA_ERR_STATE; }
+  if (use_device(c)) return TRPA_ERR_CUDA;
+  CK(cudaMemcpyAsync(out, c->d_results.p, sizeof(trpa_result) * c->n_segs, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int trpa_predict_batch(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands,
+                       uint32_t n_cands, trpa_result* out) {
+  int rc = trpa_batch_upload(c, segs, n_segs, cands, n_cands);
+  if (rc) return rc;
+  rc = trpa_batch_run(c);
+  if (rc) return rc;
+  return trpa_batch_download(c, out);
+}
+
+// ----------------------------------------------------------------------- lower-level entry points
+static int upload_table(trpa_ctx* c, const char* chars, const uint64_t* off, const uint32_t* len, uint32_t n_seq,
+                        DevBuf<uint8_t>& d_chars, DevBuf<u64>& d_off, u64* nchars_out) {
+  u64 nchars = 0;
+  for (u32 i = 0; i < n_seq; ++i) nchars = std::max<u64>(nchars, off[i] + len[i]);
+  if (d_chars.ensure(nchars + 1) || d_off.ensure(n_seq + 1)) return TRPA_ERR_NOMEM;
+  CK(cudaMemcpyAsync(d_chars.p, chars, nchars, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_off.p, off, 8ull * n_seq, cudaMemcpyHostToDevice, c->stream));
+  *nchars_out = nchars;
+  return 0;
+}
+
+int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off, const uint32_t* len, uint32_t n_seq,
+                             const uint32_t* pair_a, const uint32_t* pair_b, uint32_t n_pairs, int32_t* out_dist,
+                             int repeat, double* kernel_ms) {
+  if (!c || !chars || !off || !len || !pair_a || !pair_b || !out_dist) { set_error("bad arguments"); return TRPA_ERR_ARG; }
+  if (use_device(c)) return TRPA_ERR_CUDA;
+  if (n_pairs == 0) return 0;
+  for (u32 k = 0; k < n_pairs; ++k)
+    if (pair_a[k] >= n_seq || pair_b[k] >= n_seq) { set_error("pair index out of range"); return TRPA_ERR_ARG; }
+  DevBuf<uint8_t> d_chars; DevBuf<u64> d_off; u64 nchars = 0;
+  int rc = upload_table(c, chars, off, len, n_seq, d_chars, d_off, &nchars);
+  if (rc) return rc;
+  std::vector<SeqDesc> sd(n_seq);
+  u64 words = 0; u32 max_len = 0;
+  for (u32 i = 0; i < n_seq; ++i) { sd[i] = SeqDesc{(u32)words, len[i], 0, 0}; words += ((u64)len[i] + 31) / 32; max_len = std::max(max_len, len[i]); }
+  if (words >= 0xffffffffull) { set_error("table too large"); return TRPA_ERR_ARG; }
+  DevBuf<SeqDesc> d_sd; DevBuf<uint2> planes; DevBuf<u32> nplane; DevBuf<PairDesc> d_pairs, d_sorted; DevBuf<int32_t> d_out;
+  DevBuf<u32> d_cnt;
+  if (d_sd.ensure(n_seq + 1) || planes.ensure(words + 2) || nplane.ensure(words + 2) || d_pairs.ensure(n_pairs) ||
+      d_sorted.ensure(n_pairs) || d_out.ensure(n_pairs) || d_cnt.ensure(kNumCounters) || c->d_hist.ensure(2 * kNumShapes) ||
+      c->d_buckets.ensure(kNumShapes))
+    return TRPA_ERR_NOMEM;
+  CK(cudaMemcpyAsync(d_sd.p, sd.data(), sizeof(SeqDesc) * n_seq, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(planes.p, 0, (words + 2) * sizeof(uint2), c->stream));
+  CK(cudaMemsetAsync(nplane.p, 0, (words + 2) * sizeof(u32), c->stream));
+  // flags live inside the descriptor table (3rd u32 of each 16-byte entry): pass a strided view
+  DevBuf<u32> d_flags;
+  if (d_flags.ensure(n_seq + 1)) return TRPA_ERR_NOMEM;
+  CK(cudaMemsetAsync(d_flags.p, 0, sizeof(u32) * (n_seq + 1), c->stream));
+  CK(launch_pack_nt(d_chars.p, d_off.p, d_sd.p, n_seq, words, planes.p, nplane.p, d_flags.p, c->stream));
+  std::vector<u32> h_flags(n_seq);
+  CK(cudaMemcpyAsync(h_flags.data(), d_flags.p, sizeof(u32) * n_seq, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (u32 i = 0; i < n_seq; ++i) sd[i].flags = h_flags[i];
+  CK(cudaMemcpyAsync(d_sd.p, sd.data(), sizeof(SeqDesc) * n_seq, cudaMemcpyHostToDevice, c->stream));
+  std::vector<PairDesc> hp(n_pairs);
+  std::vector<u32> geom(kNumW * kNumL, 0);
+  for (u32 k = 0; k < n_pairs; ++k) {
+    hp[k] = PairDesc{pair_a[k], pair_b[k], k, 0};
+    const u32 m = std::min(len[pair_a[k]], len[pair_b[k]]);
+    geom[choose_shape((m + 31) / 32, 0)]++;
+  }
+  std::vector<u32> cnt(kNumCounters, 0);
+  cnt[CN_PAIRS] = n_pairs;
+  CK(cudaMemcpyAsync(d_pairs.p, hp.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_cnt.p, cnt.data(), sizeof(u32) * kNumCounters, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(c->d_hist.p, 0, sizeof(u32) * 2 * kNumShapes, c->stream));
+  const u32 blocks = std::min<u32>((n_pairs + 255) / 256, 148 * 8);
+  classify_kernel<<<blocks, 256, 0, c->stream>>>(d_pairs.p, d_cnt.p, d_sd.p, c->d_hist.p);
+  scan_kernel<<<1, 32, 0, c->stream>>>(c->d_hist.p, c->d_buckets.p);
+  scatter_kernel<<<blocks, 256, 0, c->stream>>>(d_pairs.p, d_cnt.p, c->d_hist.p, d_sorted.p);
+  CK(cudaGetLastError());
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  if (repeat < 1) repeat = 1;
+  // one untimed pass when timing is requested
+  if (kernel_ms && repeat > 1) {
+    rc = launch_myers_buckets(c, geom.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
+    if (rc) return rc;
+  }
+  CK(cudaEventRecord(e0, c->stream));
+  for (int r = 0; r < repeat; ++r) {
+    rc = launch_myers_buckets(c, geom.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
+    if (rc) return rc;
+  }
+  CK(cudaEventRecord(e1, c->stream));
+  CK(cudaMemcpyAsync(out_dist, d_out.p, sizeof(int32_t) * n_pairs, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  if (kernel_ms) *kernel_ms = ms / repeat;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  d_chars.release(); d_off.release(); d_sd.release(); planes.release(); nplane.release(); d_pairs.release();
+  d_sorted.release(); d_out.release(); d_cnt.release(); d_flags.release();
+  return 0;
+}
+
+int trpa_protein_align_batch(trpa_ctx* c, const char* chars, const uint64_t* off, const uint32_t* len, uint32_t n_seq,
+                             const uint32_t* pair_a, const uint32_t* pair_b, uint32_t n_pairs, int32_t* out3,
+                             int repeat, double* kernel_ms) {
+  if (!c || !chars || !off || !len || !pair_a || !pair_b || !out3) { set_error("bad arguments"); return TRPA_ERR_ARG; }
+  if (use_device(c)) return TRPA_ERR_CUDA;
+  if (n_pairs == 0) return 0;
+  for (u32 k = 0; k < n_pairs; ++k)
+    if (pair_a[k] >= n_seq || pair_b[k] >= n_seq) { set_error("pair index out of range"); return TRPA_ERR_ARG; }
+  DevBuf<uint8_t> d_chars, d_codes; DevBuf<u64> d_off; u64 nchars = 0;
+  int rc = upload_table(c, chars, off, len, n_seq, d_chars, d_off, &nchars);
+  if (rc) return rc;
+  if (nchars >= 0xffffffffull) { set_error("table too large"); return TRPA_ERR_ARG; }
+  std::vector<SeqDesc> sd(n_seq);
+  u32 max_len = 0;
+  for (u32 i = 0; i < n_seq; ++i) { sd[i] = SeqDesc{(u32)off[i], len[i], 0, 0}; max_len = std::max(max_len, len[i]); }
+  DevBuf<SeqDesc> d_sd; DevBuf<PairDesc> d_pairs; DevBuf<int2> d_out;
+  if (d_codes.ensure(nchars + 1) || d_sd.ensure(n_seq + 1) || d_pairs.ensure(n_pairs) || d_out.ensure(n_pairs)) return TRPA_ERR_NOMEM;
+  CK(ensure_blosum_constant(c->device));
+  CK(launch_aa_codes(d_chars.p, d_codes.p, nchars, c->stream));
+  CK(cudaMemcpyAsync(d_sd.p, sd.data(), sizeof(SeqDesc) * n_seq, cudaMemcpyHostToDevice, c->stream));
+  CK(launch_selfscore(d_sd.p, n_seq, d_codes.p, c->stream));
+  std::vector<PairDesc> hp(n_pairs);
+  for (u32 k = 0; k < n_pairs; ++k) hp[k] = PairDesc{pair_a[k], pair_b[k], k, 0};
+  CK(cudaMemcpyAsync(d_pairs.p, hp.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, c->stream));
+  int2* scr = nullptr; u32 stride = 0;
+  if (max_len > 512) {
+    stride = max_len + 2;
+    if (c->scratch_aa.ensure((size_t)n_pairs * stride)) return TRPA_ERR_NOMEM;
+    scr = c->scratch_aa.p;
+  }
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  if (repeat < 1) repeat = 1;
+  if (kernel_ms && repeat > 1) CK(launch_protein(d_pairs.p, n_pairs, d_sd.p, d_codes.p, d_out.p, scr, stride, c->stream));
+  CK(cudaEventRecord(e0, c->stream));
+  for (int r = 0; r < repeat; ++r) CK(launch_protein(d_pairs.p, n_pairs, d_sd.p, d_codes.p, d_out.p, scr, stride, c->stream));
+  CK(cudaEventRecord(e1, c->stream));
+  std::vector<int2> ho(n_pairs);
+  CK(cudaMemcpyAsync(ho.data(), d_out.p, sizeof(int2) * n_pairs, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(sd.data(), d_sd.p, sizeof(SeqDesc) * n_seq, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  if (kernel_ms) *kernel_ms = ms / repeat;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  for (u32 k = 0; k < n_pairs; ++k) {
+    out3[3 * k + 0] = ho[k].x;
+    out3[3 * k + 1] = (int)sd[pair_a[k]].pad + (int)sd[pair_b[k]].pad;
+    out3[3 * k + 2] = (int)len[pair_a[k]] + (int)len[pair_b[k]] - ho[k].y;
+  }
+  d_chars.release(); d_codes.release(); d_off.release(); d_sd.release(); d_pairs.release(); d_out.release();
+  return 0;
+}
+
+int trpa_fetch_segments(trpa_ctx* c, const uint32_t* ref_seq, const uint32_t* start, const uint32_t* stop,
+                        const uint32_t* left_ext, const uint32_t* right_ext, uint32_t n, uint8_t* out_codes,
+                        uint64_t out_capacity, uint64_t* out_off, uint32_t* out_len) {
+  if (!c || !ref_seq || !start || !stop || !left_ext || !right_ext || !out_codes || !out_off || !out_len) { set_error("bad arguments"); return TRPA_ERR_ARG; }
+  if (use_device(c)) return TRPA_ERR_CUDA;
+  const Store& R = c->store[TRPA_STORE_REF];
+  if (R.alphabet < 0) { set_error("reference store not loaded"); return TRPA_ERR_STATE; }
+  const bool protein = R.alphabet == TRPA_ALPHA_AA;
+  std::vector<u32> rlen(R.n_seq);
+  CK(cudaMemcpyAsync(rlen.data(), R.len.p, 4ull * R.n_seq, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  std::vector<SeqDesc> sd(n); std::vector<StageReq> rq(n);
+  u64 units = 0, total = 0;
+  for (u32 i = 0; i < n; ++i) {
+    if (ref_seq[i] >= R.n_seq || start[i] == 0 || stop[i] == 0) { set_error("bad fetch request"); return TRPA_ERR_ARG; }
+    // same arithmetic as Machine::stage_candidate / emit_stage (hh:870-880)
+    u64 ns, ne; u32 rev = 0;
+    if (start[i] <= stop[i]) { ns = left_ext[i] < start[i] ? start[i] - left_ext[i] : 1; ne = (u64)stop[i] + right_ext[i]; }
+    else { ns = right_ext[i] < stop[i] ? stop[i] - right_ext[i] : 1; ne = (u64)start[i] + left_ext[i]; rev = protein ? 0 : 1; }
+    const u64 L = rlen[ref_seq[i]];
+    if (ne > L) ne = L;
+    u64 b = ns - 1; if (b > L) b = L;
+    u64 e = ne > b ? ne : b; if (e > L) e = L;
+    const u32 len = (u32)(e - b);
+    sd[i] = SeqDesc{(u32)units, len, 0, 0};
+    rq[i] = StageReq{i, 1, ref_seq[i], (u32)b, rev};
+    units += protein ? ((len + 3u) & ~3u) : ((len + 31u) >> 5);
+    out_off[i] = total; out_len[i] = len; total += len;
+  }
+  if (total > out_capacity) { set_error("output buffer too small"); return TRPA_ERR_ARG; }
+  if (units >= 0xffffffffull) { set_error("fetch too large"); return TRPA_ERR_ARG; }
+  DevBuf<SeqDesc> d_sd; DevBuf<StageReq> d_rq; DevBuf<uint8_t> d_out; DevBuf<u64> d_ooff;
+  if (d_sd.ensure(n + 1) || d_rq.ensure(n + 1) || d_out.ensure(total + 16) || d_ooff.ensure(n + 1)) return TRPA_ERR_NOMEM;
+  CK(cudaMemcpyAsync(d_sd.p, sd.data(), sizeof(SeqDesc) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_rq.p, rq.data(), sizeof(StageReq) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_ooff.p, out_off, 8ull * n, cudaMemcpyHostToDevice, c->stream));
+  if (protein) {
+    DevBuf<uint8_t> stg;
+    if (stg.ensure(units + 16)) return TRPA_ERR_NOMEM;
+    CK(ensure_blosum_constant(c->device));
+    CK(launch_stage_aa(d_rq.p, n, nullptr, nullptr, R.packed.p, R.woff.p, d_sd.p, stg.p, c->stream));
+    for (u32 i = 0; i < n; ++i)
+      if (out_len[i]) CK(cudaMemcpyAsync(d_out.p + out_off[i], stg.p + sd[i].woff, out_len[i], cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(out_codes, d_out.p, total, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    stg.release();
+  } else {
+    DevBuf<uint2> pl; DevBuf<u32> pn;
+    if (pl.ensure(units + 2) || pn.ensure(units + 2)) return TRPA_ERR_NOMEM;
+    CK(launch_stage_nt(d_rq.p, n, nullptr, nullptr, nullptr, R.planes.p, R.nplane.p, R.woff.p, d_sd.p, pl.p, pn.p, c->stream));
+    CK(launch_unstage_nt(d_sd.p, n, pl.p, pn.p, d_ooff.p, d_out.p, c->stream));
+    CK(cudaMemcpyAsync(out_codes, d_out.p, total, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    pl.release(); pn.release();
+  }
+  d_sd.release(); d_rq.release(); d_out.release(); d_ooff.release();
+  return 0;
+}
+
+int trpa_lca_batch(trpa_ctx* c, const uint32_t* a, const uint32_t* b, uint32_t n, uint32_t* out) {
+  if (!c || !a || !b || !out) { set_error("bad arguments"); return TRPA_ERR_ARG; }
+  if (c->n_nodes == 0) { set_error("taxonomy not loaded"); return TRPA_ERR_STATE; }
+  if (use_device(c)) return TRPA_ERR_CUDA;
+  for (u32 i = 0; i < n; ++i) if (a[i] >= c->n_nodes || b[i] >= c->n_nodes) { set_error("node out of range"); return TRPA_ERR_ARG; }
+  if (n == 0) return 0;
+  DevBuf<u32> da, db, dout;
+  if (da.ensure(n) || db.ensure(n) || dout.ensure(n)) return TRPA_ERR_NOMEM;
+  CK(cudaMemcpyAsync(da.p, a, 4ull * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(db.p, b, 4ull * n, cudaMemcpyHostToDevice, c->stream));
+  lca_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(dev_tax(c), da.p, db.p, n, dout.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, dout.p, 4ull * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  da.release(); db.release(); dout.release();
+  return 0;
+}
+
+int trpa_int_alu_peak(trpa_ctx* c, double* lane_ops_per_s) {
+  if (!c || !lane_ops_per_s) { set_error("bad arguments"); return TRPA_ERR_ARG; }
+  if (use_device(c)) return TRPA_ERR_CUDA;
+  DevBuf<u32> sink;
+  if (sink.ensure(4)) return TRPA_ERR_NOMEM;
+  int blocks = 0, threads = 0;
+  const int iters = 20000;
+  CK(launch_alu_probe(sink.p, 2000, c->stream, &blocks, &threads));  // warm-up
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 3; ++rep) {
+    CK(cudaEventRecord(e0, c->stream));
+    CK(launch_alu_probe(sink.p, iters, c->stream, &blocks, &threads));
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double ops = (double)blocks * threads * (double)iters * alu_probe_ops_per_iter();
+    best = std::max(best, ops / (ms * 1e-3));
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  sink.release();
+  *lane_ops_per_s = best;
+  return 0;
+}
+
+}  // extern "C"

@@ -9,13 +9,5 @@ namespace trpa {
 typedef uint32_t u32;
 typedef uint64_t u64;
 
-#define TRPA_CUDA_OK(expr)                                                   \
-  do {                                                                       \
-    cudaError_t _e = (expr);                                                 \
-    if (_e != cudaSuccess) {                                                 \
-      trpa::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));  \
-      return -1;                                                             \
-    }                                                                        \
-  } while (0)
 
 }  // namespace trpa

@@ -141,11 +141,19 @@ __device__ __forceinline__ void myers_column(u32 (&VP)[W], u32 (&VN)[W], const u
 
 // pairs[first .. first+count) all use the same (L, W) shape.  L lanes per pair.
 // scratch: 3*scratch_stride words per sub-warp group slot (only used when a pair needs >1 strip).
+// bucket (nullable): device-side {start, count} of this shape inside `pairs` (written by the
+// bucketing kernels of the round); then `count` is only the host's upper bound used for the grid.
 template <int W, bool HASN>
 __global__ void __launch_bounds__(128)
 myers_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __restrict__ seqs,
              const uint2* __restrict__ planes, const u32* __restrict__ nplane, int* __restrict__ out,
-             int L, u32* __restrict__ scratch, u32 scratch_stride) {
+             int L, u32* __restrict__ scratch, u32 scratch_stride, const uint2* __restrict__ bucket) {
+  if (bucket) {
+    const uint2 bk = *bucket;
+    pairs += bk.x;
+    count = bk.y;
+    if ((blockIdx.x * blockDim.x >> 5) * (32 / L) >= count) return;
+  }
   const u32 lane = threadIdx.x & 31;
   const u32 G = 32 / L;                 // pairs per warp
   const u32 g = lane / L;               // group in warp

@@ -1,0 +1,184 @@
+"""ctypes binding of the C ABI (include/taxator_rpa_b200.h) for tests and bench.py.
+
+This is a thin mirror of the header: every method maps 1:1 to an exported symbol.  There is no
+CPU path here; creating a context without a CUDA device raises."""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(HERE), "lib", "libtaxator_rpa_b200.so")
+
+CAND_DTYPE = np.dtype([("ref_seq", "<u4"), ("rstart", "<u4"), ("rstop", "<u4"), ("qstart", "<u4"), ("qstop", "<u4"),
+                       ("score", "<f4"), ("identities", "<u4"), ("alnlen", "<u4"), ("node", "<u4")])
+SEG_DTYPE = np.dtype([("query_seq", "<u4"), ("cand_begin", "<u4"), ("cand_count", "<u4"), ("reserved", "<u4")])
+RESULT_DTYPE = np.dtype([("qrstart", "<u4"), ("qrstop", "<u4"), ("lower_node", "<u4"), ("upper_node", "<u4"),
+                         ("rtax_node", "<u4"), ("support", "<u4"), ("ival", "<f4"), ("signal", "<f4"),
+                         ("n_pass0", "<u4"), ("n_pass1", "<u4"), ("n_pass2", "<u4"), ("kind", "<u4"),
+                         ("cells", "<u8")])
+assert CAND_DTYPE.itemsize == 36 and SEG_DTYPE.itemsize == 16 and RESULT_DTYPE.itemsize == 56
+
+
+class Profile(ctypes.Structure):
+    _fields_ = [("ms_edit_distance", ctypes.c_double), ("launches_edit_distance", ctypes.c_uint64),
+                ("cells_edit_distance", ctypes.c_uint64),
+                ("ms_protein", ctypes.c_double), ("launches_protein", ctypes.c_uint64), ("cells_protein", ctypes.c_uint64),
+                ("ms_stage", ctypes.c_double), ("launches_stage", ctypes.c_uint64), ("bytes_stage", ctypes.c_uint64),
+                ("ms_decide", ctypes.c_double), ("launches_decide", ctypes.c_uint64),
+                ("ms_other", ctypes.c_double), ("launches_other", ctypes.c_uint64),
+                ("rounds", ctypes.c_uint64), ("pairs", ctypes.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = ["trpa_abi_version", "trpa_last_error", "trpa_create", "trpa_destroy", "trpa_set_params",
+           "trpa_set_arena_bytes", "trpa_profile_reset", "trpa_profile_get", "trpa_load_taxonomy", "trpa_load_store",
+           "trpa_predict_batch", "trpa_batch_upload", "trpa_batch_run", "trpa_batch_download",
+           "trpa_edit_distance_batch", "trpa_protein_align_batch", "trpa_fetch_segments", "trpa_lca_batch",
+           "trpa_int_alu_peak"]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("CUDA extension %s is missing: run `make -C taxator-tk_b200` (or __graft_entry__.build())"
+                               % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.trpa_last_error.restype = ctypes.c_char_p
+        L.trpa_create.restype = ctypes.c_void_p
+        L.trpa_create.argtypes = [ctypes.c_int, ctypes.c_void_p]
+        L.trpa_destroy.argtypes = [ctypes.c_void_p]
+        L.trpa_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+class TrpaError(RuntimeError):
+    pass
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Context:
+    def __init__(self, device=0, stream=None):
+        L = lib()
+        self.L = L
+        self.h = L.trpa_create(int(device), ctypes.c_void_p(stream) if stream else None)
+        if not self.h:
+            raise TrpaError(L.trpa_last_error().decode())
+        self.h = ctypes.c_void_p(self.h)
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.L.trpa_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TrpaError("rc=%d: %s" % (rc, self.L.trpa_last_error().decode()))
+
+    def set_params(self, exclude_factor=0.5, toppercent=0.05):
+        self._ck(self.L.trpa_set_params(self.h, ctypes.c_float(exclude_factor), ctypes.c_float(toppercent)))
+
+    def set_arena_bytes(self, nbytes):
+        self._ck(self.L.trpa_set_arena_bytes(self.h, ctypes.c_uint64(int(nbytes))))
+
+    def load_taxonomy(self, parent, left, right, depth, root=0):
+        parent = np.ascontiguousarray(parent, np.uint32); left = np.ascontiguousarray(left, np.uint32)
+        right = np.ascontiguousarray(right, np.uint32); depth = np.ascontiguousarray(depth, np.uint8)
+        self._ck(self.L.trpa_load_taxonomy(self.h, _p(parent), _p(left), _p(right), _p(depth),
+                                           ctypes.c_uint32(len(parent)), ctypes.c_uint32(root)))
+
+    def load_store(self, store, alphabet, chars, off, lens):
+        chars = np.ascontiguousarray(chars, np.uint8); off = np.ascontiguousarray(off, np.uint64)
+        lens = np.ascontiguousarray(lens, np.uint32)
+        self._ck(self.L.trpa_load_store(self.h, int(store), int(alphabet), _p(chars), _p(off), _p(lens),
+                                        ctypes.c_uint32(len(lens))))
+
+    def predict_batch(self, segs, cands):
+        segs = np.ascontiguousarray(segs, SEG_DTYPE); cands = np.ascontiguousarray(cands, CAND_DTYPE)
+        out = np.zeros(len(segs), RESULT_DTYPE)
+        self._ck(self.L.trpa_predict_batch(self.h, _p(segs), ctypes.c_uint32(len(segs)), _p(cands),
+                                           ctypes.c_uint32(len(cands)), _p(out)))
+        return out
+
+    def batch_upload(self, segs, cands):
+        segs = np.ascontiguousarray(segs, SEG_DTYPE); cands = np.ascontiguousarray(cands, CAND_DTYPE)
+        self._n_segs = len(segs)
+        self._ck(self.L.trpa_batch_upload(self.h, _p(segs), ctypes.c_uint32(len(segs)), _p(cands),
+                                          ctypes.c_uint32(len(cands))))
+
+    def batch_run(self):
+        self._ck(self.L.trpa_batch_run(self.h))
+
+    def batch_download(self, out=None):
+        if out is None:
+            out = np.zeros(self._n_segs, RESULT_DTYPE)
+        self._ck(self.L.trpa_batch_download(self.h, _p(out)))
+        return out
+
+    def profile_reset(self):
+        self._ck(self.L.trpa_profile_reset(self.h))
+
+    def profile(self):
+        p = Profile()
+        self._ck(self.L.trpa_profile_get(self.h, ctypes.byref(p)))
+        return p.as_dict()
+
+    def edit_distance_batch(self, chars, off, lens, pa, pb, repeat=1):
+        chars = np.ascontiguousarray(chars, np.uint8); off = np.ascontiguousarray(off, np.uint64)
+        lens = np.ascontiguousarray(lens, np.uint32)
+        pa = np.ascontiguousarray(pa, np.uint32); pb = np.ascontiguousarray(pb, np.uint32)
+        out = np.zeros(len(pa), np.int32)
+        ms = ctypes.c_double(0)
+        self._ck(self.L.trpa_edit_distance_batch(self.h, _p(chars), _p(off), _p(lens), ctypes.c_uint32(len(lens)),
+                                                 _p(pa), _p(pb), ctypes.c_uint32(len(pa)), _p(out), int(repeat),
+                                                 ctypes.byref(ms)))
+        return out, ms.value
+
+    def protein_align_batch(self, chars, off, lens, pa, pb, repeat=1):
+        chars = np.ascontiguousarray(chars, np.uint8); off = np.ascontiguousarray(off, np.uint64)
+        lens = np.ascontiguousarray(lens, np.uint32)
+        pa = np.ascontiguousarray(pa, np.uint32); pb = np.ascontiguousarray(pb, np.uint32)
+        out = np.zeros((len(pa), 3), np.int32)
+        ms = ctypes.c_double(0)
+        self._ck(self.L.trpa_protein_align_batch(self.h, _p(chars), _p(off), _p(lens), ctypes.c_uint32(len(lens)),
+                                                 _p(pa), _p(pb), ctypes.c_uint32(len(pa)), _p(out), int(repeat),
+                                                 ctypes.byref(ms)))
+        return out, ms.value
+
+    def fetch_segments(self, ref_seq, start, stop, left_ext, right_ext):
+        arrs = [np.ascontiguousarray(a, np.uint32) for a in (ref_seq, start, stop, left_ext, right_ext)]
+        n = len(arrs[0])
+        span = np.abs(arrs[1].astype(np.int64) - arrs[2].astype(np.int64)) + 1 + arrs[3] + arrs[4]
+        cap = int(span.sum()) + 16
+        out = np.zeros(cap, np.uint8)
+        ooff = np.zeros(n, np.uint64); olen = np.zeros(n, np.uint32)
+        self._ck(self.L.trpa_fetch_segments(self.h, *[_p(a) for a in arrs], ctypes.c_uint32(n), _p(out),
+                                            ctypes.c_uint64(cap), _p(ooff), _p(olen)))
+        return [out[int(o):int(o) + int(l)] for o, l in zip(ooff, olen)]
+
+    def lca_batch(self, a, b):
+        a = np.ascontiguousarray(a, np.uint32); b = np.ascontiguousarray(b, np.uint32)
+        out = np.zeros(len(a), np.uint32)
+        self._ck(self.L.trpa_lca_batch(self.h, _p(a), _p(b), ctypes.c_uint32(len(a)), _p(out)))
+        return out
+
+    def int_alu_peak(self):
+        v = ctypes.c_double(0)
+        self._ck(self.L.trpa_int_alu_peak(self.h, ctypes.byref(v)))
+        return v.value

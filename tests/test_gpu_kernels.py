@@ -1,0 +1,117 @@
+"""GPU parity tests of the low-level C-ABI entry points against the oracle (bit-exact)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+
+def _table(seqs):
+    lens = np.array([len(s) for s in seqs], np.uint32)
+    off = np.zeros(len(seqs), np.uint64)
+    off[1:] = np.cumsum(lens[:-1].astype(np.uint64))
+    chars = np.concatenate([np.frombuffer(s, np.uint8) for s in seqs]) if seqs else np.zeros(0, np.uint8)
+    return chars, off, lens
+
+
+def _mutate(rng, s, rate, alpha):
+    a = np.frombuffer(s, np.uint8).copy()
+    r = rng.random(len(a))
+    reps = np.ones(len(a), np.int64)
+    reps[r < rate / 3] = 0
+    reps[(r >= rate / 3) & (r < 2 * rate / 3)] = 2
+    sub = (r >= 2 * rate / 3) & (r < rate)
+    a[sub] = alpha[rng.integers(0, len(alpha), int(sub.sum()))]
+    out = np.repeat(a, reps)
+    ends = np.cumsum(reps)
+    pos = ends[reps == 2] - 1
+    out[pos] = alpha[rng.integers(0, len(alpha), len(pos))]
+    return out.tobytes()
+
+
+def _oracle_ed(a, b):
+    O = ol.oracle()
+    ca = ol.codes_of(np.frombuffer(a, np.uint8), False)
+    cb = ol.codes_of(np.frombuffer(b, np.uint8), False)
+    return O.orc_edit_distance(ol.ptr(ca, ol.u8p), len(ca), ol.ptr(cb, ol.u8p), len(cb))
+
+
+@pytest.mark.parametrize("with_n", [False, True])
+def test_edit_distance_lengths(ctx, with_n):
+    rng = np.random.default_rng(7 + with_n)
+    alpha = np.frombuffer(b"ACGTN" if with_n else b"ACGT", np.uint8)
+    seqs, pa, pb = [], [], []
+    lens = [0, 1, 2, 31, 32, 33, 63, 64, 65, 95, 96, 97, 127, 128, 129, 255, 256, 257, 383, 384, 385, 500, 511, 512,
+            513, 767, 768, 769, 1000, 1023, 1024, 1025, 1500, 2047, 2048, 2049, 3000, 4095, 4096, 4097, 5000, 6143, 6144,
+            6145, 8000, 10000, 12288, 12289, 16384, 20000, 24576, 24577, 30000, 40000, 50000]
+    for L in lens:
+        a = alpha[rng.integers(0, len(alpha), L)].tobytes()
+        for rate in (0.0, 0.05, 0.3):
+            b = _mutate(rng, a, rate, alpha)
+            seqs += [a, b]
+            pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)
+        # unrelated, different length
+        c = alpha[rng.integers(0, len(alpha), int(rng.integers(0, max(2, L))))].tobytes()
+        seqs.append(c)
+        pa.append(len(seqs) - 1); pb.append(len(seqs) - 4)
+    chars, off, ln = _table(seqs)
+    got, _ = ctx.edit_distance_batch(chars, off, ln, pa, pb)
+    for k in range(len(pa)):
+        want = _oracle_ed(seqs[pa[k]], seqs[pb[k]])
+        assert got[k] == want, (k, len(seqs[pa[k]]), len(seqs[pb[k]]), int(got[k]), want)
+
+
+def test_edit_distance_many_random(ctx):
+    rng = np.random.default_rng(11)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    seqs, pa, pb = [], [], []
+    for _ in range(3000):
+        L = int(rng.integers(1, 1500))
+        a = alpha[rng.integers(0, 4, L)].tobytes()
+        b = _mutate(rng, a, float(rng.uniform(0, 0.4)), alpha)
+        seqs += [a, b]
+        pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)
+    chars, off, ln = _table(seqs)
+    got, _ = ctx.edit_distance_batch(chars, off, ln, pa, pb)
+    want = np.array([_oracle_ed(seqs[a], seqs[b]) for a, b in zip(pa, pb)], np.int32)
+    assert np.array_equal(got, want), np.flatnonzero(got != want)[:10]
+
+
+def test_edit_distance_lowercase_and_iupac(ctx):
+    seqs = [b"acgtACGTnNRYKMuU--", b"ACGTACGTNNNNNNTT", b"", b"A"]
+    chars, off, ln = _table(seqs)
+    pa, pb = [0, 0, 2, 3, 2], [1, 0, 3, 1, 2]
+    got, _ = ctx.edit_distance_batch(chars, off, ln, pa, pb)
+    want = [_oracle_ed(seqs[a], seqs[b]) for a, b in zip(pa, pb)]
+    assert got.tolist() == want
+
+
+def test_protein_align(ctx):
+    rng = np.random.default_rng(5)
+    O = ol.oracle()
+    full = np.frombuffer(b"ABCDEFGHIJKLMNOPQRSTUVWYZX*", np.uint8)
+    aa20 = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
+    seqs, pa, pb = [], [], []
+    for t in range(500):
+        alpha = full if t % 4 == 0 else aa20
+        L = int(rng.choice([1, 2, 5, 31, 32, 33, 100, 299, 300, 301, 400, 511, 512, 513, 600, 1100]))
+        a = alpha[rng.integers(0, len(alpha), L)].tobytes()
+        if t % 2:
+            b = _mutate(rng, a, float(rng.choice([0.0, 0.1, 0.4, 0.8])), alpha)
+            if len(b) == 0:
+                b = b"A"
+        else:
+            b = alpha[rng.integers(0, len(alpha), int(rng.integers(1, 700)))].tobytes()
+        seqs += [a, b]
+        pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)
+    chars, off, ln = _table(seqs)
+    got, _ = ctx.protein_align_batch(chars, off, ln, pa, pb)
+    out6 = (ctypes.c_int * 6)()
+    for k in range(len(pa)):
+        ca = ol.codes_of(np.frombuffer(seqs[pa[k]], np.uint8), True)
+        cb = ol.codes_of(np.frombuffer(seqs[pb[k]], np.uint8), True)
+        O.orc_protein_align(ol.ptr(ca, ol.u8p), len(ca), ol.ptr(cb, ol.u8p), len(cb), out6)
+        assert got[k].tolist() == [out6[0], out6[1], out6[2]], (k, len(ca), len(cb), got[k].tolist(), list(out6))

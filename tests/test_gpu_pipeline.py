@@ -1,0 +1,79 @@
+"""GPU parity of the whole batched RPA path (decide/stage/align rounds) against the oracle."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def load(ctx, fd):
+    ctx.load_taxonomy(fd.parent, fd.left, fd.right, fd.depth, 0)
+    alpha = 1 if fd.protein else 0
+    ctx.load_store(0, alpha, fd.q_chars, fd.q_off, fd.q_len)
+    ctx.load_store(1, alpha, fd.r_chars, fd.r_off, fd.r_len)
+
+
+CASES = [
+    dict(seed=1, protein=False, n_genomes=60, genome_len=3000, n_queries=150, query_len=(200, 600), n_cand=25,
+         levels=(2, 4, 6, 10, 20), multi_segment_frac=0.2, frac_n=0.002),
+    dict(seed=2, protein=False, n_genomes=80, genome_len=8000, n_queries=120, query_len=(900, 2500), n_cand=30,
+         levels=(2, 4, 6, 10, 20)),
+    dict(seed=3, protein=True, n_genomes=60, genome_len=600, n_queries=150, query_len=(80, 300), n_cand=25,
+         levels=(2, 4, 6, 10, 20), multi_segment_frac=0.2, frac_n=0.002),
+    dict(seed=4, protein=False, n_genomes=40, genome_len=4000, n_queries=100, query_len=(300, 1200), n_cand=20,
+         levels=(2, 3, 5, 8, 12), query_indel=0.1, query_sub=0.05),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "seed%d%s" % (c["seed"], "aa" if c["protein"] else "nt"))
+def test_pipeline_matches_oracle(ctx, case):
+    fd = ol.FlatData(synth.generate(synth.SynthConfig(**case)))
+    want = ol.oracle_predict(fd)
+    load(ctx, fd)
+    ctx.set_params(0.5, 0.05)
+    got = ctx.predict_batch(fd.segs, fd.cands)
+    assert ol.results_equal(want, got) == []
+
+
+def test_small_arena_chunks(ctx):
+    case = CASES[0]
+    fd = ol.FlatData(synth.generate(synth.SynthConfig(**case)))
+    want = ol.oracle_predict(fd)
+    load(ctx, fd)
+    ctx.set_arena_bytes(64 * 1024)
+    try:
+        got = ctx.predict_batch(fd.segs, fd.cands)
+    finally:
+        ctx.set_arena_bytes(0)
+    assert ol.results_equal(want, got) == []
+
+
+def test_fetch_and_lca(ctx):
+    fd = ol.FlatData(synth.generate(synth.SynthConfig(**CASES[0])))
+    load(ctx, fd)
+    O = ol.oracle()
+    rng = np.random.default_rng(3)
+    n = 300
+    ref = rng.integers(0, len(fd.r_len), n).astype(np.uint32)
+    L = fd.r_len[ref].astype(np.int64)
+    a = rng.integers(1, L + 50)
+    b = rng.integers(1, L + 50)
+    le = rng.integers(0, 60, n).astype(np.uint32)
+    re_ = rng.integers(0, 60, n).astype(np.uint32)
+    got = ctx.fetch_segments(ref, a.astype(np.uint32), b.astype(np.uint32), le, re_)
+    buf = np.zeros(int(L.max()) + 400, np.uint8)
+    for k in range(n):
+        m = O.orc_fetch_segment(ol.ptr(fd.r_codes, ol.u8p), ol.ptr(fd.r_off, ol.u64p), ol.ptr(fd.r_len, ol.u32p),
+                                len(fd.r_len), 0, int(ref[k]), int(a[k]), int(b[k]), int(le[k]), int(re_[k]),
+                                ol.ptr(buf, ol.u8p))
+        assert len(got[k]) == m and np.array_equal(got[k], buf[:m]), k
+    x = rng.integers(0, len(fd.parent), 2000).astype(np.uint32)
+    y = rng.integers(0, len(fd.parent), 2000).astype(np.uint32)
+    g = ctx.lca_batch(x, y)
+    O.orc_lca.restype = np.ctypeslib.ctypes.c_uint32
+    for k in range(len(x)):
+        w = O.orc_lca(ol.ptr(fd.parent, ol.u32p), ol.ptr(fd.left, ol.u32p), ol.ptr(fd.right, ol.u32p),
+                      ol.ptr(fd.depth, ol.u8p), len(fd.parent), 0, int(x[k]), int(y[k]))
+        assert g[k] == w

@@ -381,6 +381,17 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
     if (cands[k].qstart > cands[k].qstop || cands[k].qstart == 0) { set_error("candidate query range invalid (qstart must be >= 1 and <= qstop)"); return TRPA_ERR_ARG; }
     if (cands[k].rstart == 0 || cands[k].rstop == 0) { set_error("candidate reference coordinates are 1-based"); return TRPA_ERR_ARG; }
   }
+  // A segment whose best score is below (1-t)*best (i.e. negative) realigns nothing in pass 0 and
+  // trips assert(!qgroup.empty()) in the reference (hh:563); reject it instead of guessing.
+  {
+    const float factor = 1. - c->toppercent;
+    for (u32 s = 0; s < n_segs; ++s) {
+      if (segs[s].cand_count < 2) continue;
+      float best = cands[segs[s].cand_begin].score;
+      for (u32 k = 1; k < segs[s].cand_count; ++k) best = std::max(best, cands[segs[s].cand_begin + k].score);
+      if (!(best >= factor * best)) { set_error("segment with negative best alignment score: undefined in the reference (hh:563)"); return TRPA_ERR_ARG; }
+    }
+  }
   c->h_segs.assign(segs, segs + n_segs);
   c->h_cands.assign(cands, cands + n_cands);
   sort_candidates(c->h_segs.data(), n_segs, c->h_cands.data());

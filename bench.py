@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""Benchmark of the RPA hot path (BASELINE.json metric: query segments/s and GCUPS).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c5|tiny] [--impl ours|reference]
+
+One "step" = one pass of the whole batched RPA path (decide / stage / align rounds until every
+segment is placed) over one batch of synthetic query segments.  Default workload = BASELINE.json
+configs[1]: 100k 5-kb nucleotide segments x ~50 candidate references on one B200.
+ * value  : segments/s with the batch already resident in HBM (trpa_batch_run only)
+ * e2e    : segments/s through the C-ABI call a host makes (trpa_predict_batch: host buffers in, host
+            results out, H2D/D2H inside the timed region); the sequence stores are loaded once at
+            start-up, exactly like the reference loads its stores before the first predict()
+ * roofline: the edit-distance kernel against the measured INT32 ALU-pipe peak (integer DP is ALU
+            bound), plus roofline_hbm for the segment staging kernel
+ * cpu_baseline: the REAL reference (oracle/_ref/taxator, unmodified sources) on a bounded sample
+With --impl reference only the reference binary runs (on the host cores).
+Under torchrun every rank owns one GPU and its own shard of segments (weak scaling, no collective
+on the data path); time = max over ranks.
+"""
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "taxator-tk_b200", "python"))
+import synth  # noqa: E402
+import gff3  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "c2": dict(desc="nucleotide RPA, 100k 5-kb contig segments x ~50 candidate refs", protein=False,
+               cfg=dict(n_genomes=400, genome_len=50000, n_queries=100000, query_len=(5000, 5000), n_cand=50,
+                        levels=(4, 8, 16, 40, 100)), cpu_sample=600),
+    # configs[0] (the reference's own CPU-runnable case)
+    "c1": dict(desc="nucleotide RPA, 1k 1-kb contigs, 200-genome refpack", protein=False,
+               cfg=dict(n_genomes=200, genome_len=20000, n_queries=1000, query_len=(1000, 1000), n_cand=36,
+                        levels=(4, 8, 16, 40, 100)), cpu_sample=1000),
+    # configs[2]
+    "c3": dict(desc="protein RPA (BLOSUM62, linear gap), 50k 300-aa segments", protein=True,
+               cfg=dict(n_genomes=400, genome_len=400, n_queries=50000, query_len=(300, 300), n_cand=30,
+                        levels=(4, 8, 16, 40, 100)), cpu_sample=600),
+    # configs[4], scaled to one GPU-minute per step
+    "c5": dict(desc="long-read nucleotide RPA, 10-50 kb noisy reads (15% error)", protein=False,
+               cfg=dict(n_genomes=100, genome_len=200000, n_queries=4000, query_len=(10000, 50000), n_cand=20,
+                        levels=(2, 4, 8, 16, 40), query_sub=0.05, query_indel=0.10), cpu_sample=16),
+    "tiny": dict(desc="smoke-sized nucleotide RPA", protein=False,
+                 cfg=dict(n_genomes=60, genome_len=6000, n_queries=400, query_len=(1000, 1000), n_cand=25,
+                          levels=(2, 4, 6, 10, 20)), cpu_sample=200),
+}
+
+# ALU-pipe instructions per 32-cell word-step of the W=20 edit-distance kernel, counted in SASS
+# (profiles/r01_sass_mix.md): LOP3 + IADD3.X + SHF per word plus the per-column boundary work.
+ALU_OPS_PER_WORDSTEP = 13.9
+
+
+def make_data(workload, seed, n_queries=None):
+    w = WORKLOADS[workload]
+    cfg = dict(w["cfg"])
+    if n_queries is not None:
+        cfg["n_queries"] = n_queries
+    c = synth.SynthConfig(seed=seed, protein=w["protein"], **cfg)
+    return synth.generate_fast(c)
+
+
+class Flat:
+    def __init__(self, d):
+        self.d = d
+        self.protein = bool(d.cfg.protein)
+        self.parent, self.left, self.right, self.depth = d.nested_set()
+        self.q_chars, self.q_off, self.q_len = d.store_arrays(d.q_seqs)
+        self.r_chars, self.r_off, self.r_len = d.store_arrays(d.ref_seqs)
+        self.segs, self.cands = synth.segments_fast(d)
+
+
+def subset(d, n_queries):
+    """First n_queries queries (and their records) of a SynthData, same refpack/taxonomy."""
+    s = synth.SynthData(cfg=d.cfg)
+    s.tax_ids, s.tax_parent, s.tax_rank = d.tax_ids, d.tax_parent, d.tax_rank
+    s.ref_names, s.ref_seqs, s.ref_taxnode = d.ref_names, d.ref_seqs, d.ref_taxnode
+    s.q_names, s.q_seqs = d.q_names[:n_queries], d.q_seqs[:n_queries]
+    m = d.rec["q"] < n_queries
+    s.rec = {k: v[m] for k, v in d.rec.items()}
+    return s
+
+
+def run_reference_binary(d, threads, keep_dir=None):
+    """Times oracle/_ref/taxator (real reference, -DNDEBUG) on the files of d; returns (seconds, sorted GFF3 lines)."""
+    binary = os.path.join(ROOT, "oracle", "_ref", "taxator")
+    if not os.path.exists(binary):
+        return None, None
+    tmp = keep_dir or tempfile.mkdtemp(prefix="trpa_ref_")
+    try:
+        d.write_files(tmp)
+        env = dict(os.environ, TAXATORTK_TAXONOMY_NCBI=tmp)
+        cmd = [binary, "-a", "rpa", "-g", "mapping.tax", "-q", "query.fna", "-f", "ref.fna", "-i", "ref.fna.fai",
+               "-p", str(threads), "-x", "0.5", "-o", "0"]
+        if d.cfg.protein:
+            cmd += ["-b", "protein"]
+        with open(os.path.join(tmp, "alignments.tsv"), "rb") as fin:
+            t0 = time.perf_counter()
+            p = subprocess.run(cmd, cwd=tmp, env=env, stdin=fin, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            dt = time.perf_counter() - t0
+        if p.returncode != 0:
+            raise RuntimeError("reference binary failed: " + p.stderr.decode()[-400:])
+        lines = sorted(l + "\n" for l in p.stdout.decode().splitlines() if not l.startswith("##"))
+        return dt, lines
+    finally:
+        if keep_dir is None:
+            shutil.rmtree(tmp, ignore_errors=True)
+
+
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU implementation on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    sample = w["cpu_sample"]
+    d = make_data(args.workload, args.seed, n_queries=max(sample, 1))
+    n_seg = len(synth.segments_fast(d)[0])
+    tmp = tempfile.mkdtemp(prefix="trpa_refarm_")
+    times = []
+    try:
+        for it in range(args.warmup + args.steps):
+            dt, _ = run_reference_binary(d, cores, keep_dir=tmp)
+            if dt is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/taxator was not built"}))
+                return
+            if it >= args.warmup:
+                times.append(dt)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    ms = 1e3 * sum(times) / len(times)
+    value = n_seg / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "query segments/sec (taxator -a rpa hot path)", "value": value,
+        "unit": "segments/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32" if not w["protein"] else "int32+f32", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + w["desc"], "segments_per_step": n_seg,
+                   "note": "bounded sample of the workload, wall time of the whole binary incl. start-up"},
+        "cpu_baseline": {"value": value, "unit": "segments/s", "cores": cores, "kind": "reference",
+                         "sample": "%d segments of the workload, oracle/_ref/taxator -DNDEBUG -p %d" % (n_seg, cores)},
+        "e2e": {"value": value, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seed", type=int, default=20261017)
+    ap.add_argument("--segments", type=int, default=None, help="override segments per GPU (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import rpa_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w = WORKLOADS[args.workload]
+
+    # ---- synthetic data: every rank owns its own shard (weak scaling)
+    t0 = time.time()
+    d = make_data(args.workload, args.seed + rank, n_queries=args.segments)
+    fd = Flat(d)
+    n_seg, n_cand = len(fd.segs), len(fd.cands)
+    t_gen = time.time() - t0
+
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = rpa_b200.Context(local_rank, stream)
+    t0 = time.time()
+    ctx.load_taxonomy(fd.parent, fd.left, fd.right, fd.depth, 0)
+    alpha = 1 if fd.protein else 0
+    ctx.load_store(0, alpha, fd.q_chars, fd.q_off, fd.q_len)
+    ctx.load_store(1, alpha, fd.r_chars, fd.r_off, fd.r_len)
+    torch.cuda.synchronize()
+    t_load = time.time() - t0
+    alu_peak = ctx.int_alu_peak()
+
+    # pinned host buffers for the e2e path
+    segs_t = torch.from_numpy(fd.segs.view(np.uint8).copy()).pin_memory()
+    cands_t = torch.from_numpy(fd.cands.view(np.uint8).copy()).pin_memory()
+    out_t = torch.zeros(n_seg * rpa_b200.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    segs_p = segs_t.numpy().view(rpa_b200.SEG_DTYPE)
+    cands_p = cands_t.numpy().view(rpa_b200.CAND_DTYPE)
+    out_p = out_t.numpy().view(rpa_b200.RESULT_DTYPE)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident timing
+    ctx.batch_upload(segs_p, cands_p)
+    for _ in range(args.warmup):
+        ctx.batch_run()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.profile_reset()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ctx.batch_run()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    prof = ctx.profile()
+    res = ctx.batch_download(out_p).copy()
+    cells_step = float(res["cells"].sum())
+    pairs_step = float((res["n_pass0"] + res["n_pass1"] + res["n_pass2"]).sum())
+
+    # ---- end-to-end timing through the host-buffer C-ABI call
+    import ctypes
+    vp = ctypes.c_void_p
+
+    def predict_host():
+        return ctx.L.trpa_predict_batch(ctx.h, vp(segs_p.ctypes.data), ctypes.c_uint32(n_seg), vp(cands_p.ctypes.data),
+                                        ctypes.c_uint32(n_cand), vp(out_p.ctypes.data))
+
+    for _ in range(min(args.warmup, 1)):
+        predict_host()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        rc = predict_host()
+        assert rc == 0, ctx.L.trpa_last_error()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)))
+    clocks = sampler.finish()
+
+    total_segs = sum_over_ranks(float(n_seg))
+    total_cells = sum_over_ranks(cells_step)
+    ms_step = ms_total / args.steps
+    value = total_segs / (ms_step / 1e3)
+    e2e_value = total_segs / (ms_e2e / args.steps / 1e3)
+
+    # ---- roofline of the dominant kernel
+    if fd.protein:
+        k_ms, k_launch = prof["ms_protein"], prof["launches_protein"]
+        # measured cell rate vs a nominal 12 ALU ops per cell
+        peak = alu_peak / 12.0 / 1e9
+        kname = "protein_kernel"
+    else:
+        k_ms, k_launch = prof["ms_edit_distance"], prof["launches_edit_distance"]
+        peak = alu_peak * 32.0 / ALU_OPS_PER_WORDSTEP / 1e9
+        kname = "myers_kernel"
+    achieved = cells_step * args.steps / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
+    roofline = {"bound": "int32_alu", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GCUPS",
+                "frac": achieved / peak if peak else None, "traffic": None,
+                "peak_source": "own probe trpa_int_alu_peak (%.3e lane-ops/s) / %.1f ALU ops per 32-cell word-step"
+                               % (alu_peak, ALU_OPS_PER_WORDSTEP) if not fd.protein else "own probe / 12 ops per cell",
+                "kernel_ms_per_step": k_ms / args.steps, "kernel_share_of_step": (k_ms / args.steps) / ms_step}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline_hbm = None
+    if prof["ms_stage"] > 0:
+        # algorithmic bytes of staging: packed store bits read + staged bits written
+        # (nt: 3 planes x 4 B per 32-base word each way; aa: 5 bit read + 1 byte written per residue)
+        gbs = prof["bytes_stage"] / (prof["ms_stage"] / 1e3) / 1e9
+        roofline_hbm = {"bound": "hbm", "kernel": "stage_kernel", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": gbs / hbm_peak, "traffic": None,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                        "bytes_per_step": prof["bytes_stage"] / args.steps,
+                        "ms_per_step": prof["ms_stage"] / args.steps}
+
+    line = {
+        "metric": "query segments/sec (taxator -a rpa hot path)", "value": value, "unit": "segments/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32" if not fd.protein else "int32+f32", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + w["desc"], "segments_per_gpu": n_seg, "candidates_per_gpu": n_cand,
+                   "alignments_per_step": pairs_step, "cells_per_step": cells_step,
+                   "l2": "inputs larger than L2 (staged segments + refpack + candidate tables per step >> 126 MB)",
+                   "seed": args.seed},
+        "gcups": total_cells / (ms_step / 1e3) / 1e9,
+        "e2e": {"value": e2e_value, "unit": "segments/s", "ms_per_step": ms_e2e / args.steps,
+                "gcups": total_cells / (ms_e2e / args.steps / 1e3) / 1e9,
+                "h2d_bytes_per_step": int(segs_t.numel() + cands_t.numel()), "d2h_bytes_per_step": int(out_t.numel())},
+        "roofline": roofline,
+        "gpu_launches": int(prof["launches_edit_distance"] + prof["launches_protein"] + prof["launches_stage"] +
+                            prof["launches_decide"] + prof["launches_other"]),
+        "rounds_per_step": prof["rounds"] / args.steps,
+        "phase_ms_per_step": {"align": k_ms / args.steps, "stage": prof["ms_stage"] / args.steps,
+                              "decide": prof["ms_decide"] / args.steps, "bucket": prof["ms_other"] / args.steps},
+        "clocks": clocks,
+        "setup_s": {"generate": t_gen, "load_stores": t_load},
+    }
+    if roofline_hbm:
+        line["roofline_hbm"] = roofline_hbm
+
+    # ---- CPU baseline: the real reference on a bounded sample (rank 0, N=1 only)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        nq = min(w["cpu_sample"], len(d.q_seqs))
+        sub = subset(d, nq)
+        dt, ref_lines = run_reference_binary(sub, cores)
+        if dt is not None:
+            nseg_sub = int((fd.segs["query_seq"] < nq).sum())
+            sel = fd.segs["query_seq"] < nq
+            taxids = [str(t) for t in d.tax_ids]
+            ours = sorted(gff3.render(res[sel], fd.segs[sel], d.q_names, fd.q_len, fd.parent, fd.depth, taxids))
+            cells_sub = float(res["cells"][sel].sum())
+            line["cpu_baseline"] = {"value": nseg_sub / dt, "unit": "segments/s", "cores": cores, "kind": "reference",
+                                    "gcups": cells_sub / dt / 1e9,
+                                    "sample": "first %d segments of the workload; oracle/_ref/taxator (unmodified "
+                                              "reference, -DNDEBUG) -p %d, wall %.2f s incl. start-up" % (nseg_sub, cores, dt),
+                                    "gff3_identical_to_gpu": ours == ref_lines}
+        else:
+            line["cpu_baseline"] = {"value": None, "unit": "segments/s", "cores": cores, "kind": "reference",
+                                    "sample": "oracle/_ref/taxator missing"}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

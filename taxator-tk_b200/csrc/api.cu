@@ -498,6 +498,10 @@ int trpa_batch_run(trpa_ctx* c) {
       if (c->h_counters[CN_OVERFLOW]) { set_error("internal: staging arena overflow"); return TRPA_ERR_STATE; }
       if (n_pairs == 0) {
         if (n_active) { set_error("internal: segments active without pending alignments"); return TRPA_ERR_STATE; }
+        // algorithmic staging traffic of the chunk: packed store bits read + staged bits written
+        // (nt: 3 planes x 4 B per 32-base word each way; aa: 5 bit read + 1 byte written per residue)
+        const u64 units = c->h_counters[CN_ARENA];
+        c->prof.bytes_stage += protein ? (units * 13) / 8 : units * 24;
         break;
       }
       c->prof.rounds++;

@@ -381,3 +381,172 @@ def generate(cfg: SynthConfig, identity_fn=None) -> SynthData:
         "alnlen": np.array(R["alnlen"], np.uint32),
     }
     return d
+
+
+def generate_fast(cfg: SynthConfig, block: int = 100) -> SynthData:
+    """Vectorised generator for benchmark-sized nucleotide configs (same SynthData layout).
+
+    Differences from generate(): query windows start on `block` boundaries, candidate identities are
+    block-resolution ungapped identities of the source window (scaled by the query noise) -- they only
+    need to be plausible and tie-free, not exact -- and genomes are not truncated.  Substitution-only
+    queries (query_indel is ignored unless > 0, then a slower per-query path is used)."""
+    rng = np.random.default_rng(cfg.seed)
+    alphabet = AA20 if cfg.protein else NT
+    d = SynthData(cfg=cfg)
+    counts = list(cfg.levels) + [cfg.n_genomes]
+    ranks = RANKS[len(RANKS) - len(counts):]
+    ids, parent, rank = [1], [0], ["no rank"]
+    prev_level = [0]
+    next_id = 2
+    level_nodes = []
+    for lvl, cnt in enumerate(counts):
+        cur = []
+        for k in range(cnt):
+            p = prev_level[k] if k < len(prev_level) else prev_level[int(rng.integers(0, len(prev_level)))]
+            ids.append(next_id); parent.append(p); rank.append(ranks[lvl])
+            cur.append(len(ids) - 1)
+            next_id += 1
+        level_nodes.append(cur)
+        prev_level = cur
+    d.tax_ids = np.array(ids, dtype=np.int64)
+    d.tax_parent = np.array(parent, dtype=np.int64)
+    d.tax_rank = rank
+    G = (cfg.genome_len // block) * block
+    node_seq = {0: alphabet[rng.integers(0, len(alphabet), G)]}
+    for lvl, nodes in enumerate(level_nodes):
+        for v in nodes:
+            node_seq[v] = _mutate_subst(rng, node_seq[int(d.tax_parent[v])], rng.uniform(*cfg.edge_rate), alphabet)
+        if lvl > 0:
+            for v in level_nodes[lvl - 1]:
+                node_seq.pop(v, None)
+    species = level_nodes[-1]
+    key = []
+    for v in species:
+        path = []
+        x = v
+        while x != 0:
+            path.append(x)
+            x = int(d.tax_parent[x])
+        key.append(tuple(reversed(path)))
+    order = sorted(range(len(species)), key=lambda i: key[i])
+    species = [species[i] for i in order]
+    E = np.stack([node_seq[v] for v in species])          # (n_g, G) evolved, coordinate aligned
+    n_g = cfg.n_genomes
+    is_rev = (rng.random(n_g) < cfg.frac_rev_genomes) & (not cfg.protein)
+    d.ref_names = ["G%05d" % g for g in range(n_g)]
+    d.ref_seqs = [np.ascontiguousarray(revcomp(E[g]) if is_rev[g] else E[g]) for g in range(n_g)]
+    d.ref_taxnode = np.array(species, dtype=np.uint32)
+
+    K = min(cfg.n_cand, n_g)
+    nb = G // block
+    half = K // 2
+    # cumulative block identities between genome g and g+off, off in [-half, K-half)
+    offs = np.arange(-half, K - half)
+    cum = np.zeros((n_g, K, nb + 1), dtype=np.int32)
+    for oi, off in enumerate(offs):
+        lo, hi = max(0, -off), min(n_g, n_g - off)
+        if hi <= lo:
+            continue
+        eq = (E[lo:hi] == E[lo + off:hi + off]).reshape(hi - lo, nb, block).sum(axis=2)
+        cum[lo:hi, oi, 1:] = np.cumsum(eq, axis=1)
+
+    nq = cfg.n_queries
+    Lq = (rng.integers(cfg.query_len[0], cfg.query_len[1] + 1, nq) // block) * block
+    Lq = np.clip(Lq, block, G)
+    g0 = rng.integers(0, n_g, nq)
+    pblk = (rng.random(nq) * ((G - Lq) // block + 1)).astype(np.int64)
+    p = pblk * block
+    d.q_names = ["Q%06d" % i for i in range(nq)]
+    d.q_seqs = []
+    for i0 in range(0, nq, 4096):
+        i1 = min(nq, i0 + 4096)
+        for i in range(i0, i1):
+            src = E[g0[i], p[i]:p[i] + Lq[i]]
+            d.q_seqs.append(src)
+    # substitutions, chunked and vectorised over the concatenation
+    lens = Lq.astype(np.int64)
+    for i0 in range(0, nq, 8192):
+        i1 = min(nq, i0 + 8192)
+        cat = np.concatenate(d.q_seqs[i0:i1])
+        cat = _mutate_subst(rng, cat, cfg.query_sub, alphabet)
+        o = 0
+        for i in range(i0, i1):
+            seg = cat[o:o + lens[i]]
+            o += lens[i]
+            if cfg.query_indel > 0:
+                seg = _mutate_indel(rng, seg, cfg.query_indel, alphabet)
+            d.q_seqs[i] = np.ascontiguousarray(seg)
+    qlen_final = np.array([len(s) for s in d.q_seqs], dtype=np.int64)
+
+    # candidate genomes: window of K around g0, clipped to [0, n_g)
+    lo = np.clip(g0 - half, 0, n_g - K)
+    cand_g = lo[:, None] + np.arange(K)[None, :]                 # (nq, K)
+    off_idx = cand_g - g0[:, None] + half                         # index into offs; may fall outside for clipped windows
+    valid = (off_idx >= 0) & (off_idx < K)
+    oi = np.clip(off_idx, 0, K - 1)
+    b0 = pblk[:, None]
+    b1 = b0 + (Lq // block)[:, None]
+    ident = cum[g0[:, None], oi, b1] - cum[g0[:, None], oi, b0]   # (nq, K) exact block sums
+    ident = np.where(valid, ident, (Lq[:, None] * 0.5).astype(np.int64))
+    ident = np.round(ident * (1.0 - cfg.query_sub)).astype(np.int64)
+    # partial records
+    part = rng.random((nq, K)) < cfg.frac_partial
+    a = (rng.random((nq, K)) * (Lq[:, None] // 4)).astype(np.int64) * part
+    b = (rng.random((nq, K)) * (Lq[:, None] // 4)).astype(np.int64) * part
+    qs = 1 + a
+    qe = Lq[:, None] - b
+    alnlen = qe - qs + 1
+    ident = np.minimum((ident * alnlen) // Lq[:, None], alnlen - 1)
+    # strictly decreasing identities per query (tie-free (score, identities))
+    srt = np.argsort(-ident, axis=1, kind="stable")
+    ident_s = np.take_along_axis(ident, srt, axis=1)
+    dec = ident_s - np.arange(K)[None, :] * 0                     # enforce strict decrease
+    for k in range(1, K):
+        dec[:, k] = np.minimum(dec[:, k], dec[:, k - 1] - 1)
+    ident = np.empty_like(ident)
+    np.put_along_axis(ident, srt, dec, axis=1)
+    keep = ident > 0
+    fs = p[:, None] + qs
+    fe = p[:, None] + qe
+    rev = is_rev[cand_g]
+    rstart = np.where(rev, G - fs + 1, fs)
+    rstop = np.where(rev, G - fe + 1, fe)
+    # rescale query coordinates when indels changed the query length
+    scale = qlen_final[:, None] / Lq[:, None]
+    qs2 = np.clip(np.round(qs * scale).astype(np.int64), 1, qlen_final[:, None])
+    qe2 = np.clip(np.round(qe * scale).astype(np.int64), qs2, qlen_final[:, None])
+    qs2 = np.where(scale == 1.0, qs, qs2)
+    qe2 = np.where(scale == 1.0, qe, qe2)
+    perm = np.argsort(rng.random((nq, K)), axis=1)                # file order is not score order
+    def flat(x):
+        return np.take_along_axis(x, perm, axis=1)[np.take_along_axis(keep, perm, axis=1)]
+    qidx = np.broadcast_to(np.arange(nq)[:, None], (nq, K))
+    ident_f = flat(ident)
+    alnlen_f = flat(alnlen)
+    d.rec = {
+        "q": flat(qidx).astype(np.uint32), "qstart": flat(qs2).astype(np.uint32), "qstop": flat(qe2).astype(np.uint32),
+        "r": flat(cand_g).astype(np.uint32), "rstart": flat(rstart).astype(np.uint32),
+        "rstop": flat(rstop).astype(np.uint32),
+        "score": (2.0 * ident_f - 3.0 * (alnlen_f - ident_f)).astype(np.float32),
+        "ident": ident_f.astype(np.uint32), "alnlen": alnlen_f.astype(np.uint32),
+    }
+    return d
+
+
+def segments_fast(d: SynthData):
+    """segments() for data where every query's records overlap into ONE segment (generate_fast with
+    multi_segment_frac == 0): vectorised."""
+    r = d.rec
+    nrec = len(r["q"])
+    order = np.lexsort((np.arange(nrec), r["qstop"], r["qstart"], r["q"]))
+    q = r["q"][order]
+    cand = np.zeros(nrec, dtype=CAND_DTYPE)
+    cand["ref_seq"] = r["r"][order]; cand["rstart"] = r["rstart"][order]; cand["rstop"] = r["rstop"][order]
+    cand["qstart"] = r["qstart"][order]; cand["qstop"] = r["qstop"][order]; cand["score"] = r["score"][order]
+    cand["identities"] = r["ident"][order]; cand["alnlen"] = r["alnlen"][order]
+    cand["node"] = d.ref_taxnode[r["r"][order]]
+    starts = np.flatnonzero(np.concatenate([[True], q[1:] != q[:-1]]))
+    counts = np.diff(np.concatenate([starts, [nrec]]))
+    seg = np.zeros(len(starts), dtype=SEG_DTYPE)
+    seg["query_seq"] = q[starts]; seg["cand_begin"] = starts; seg["cand_count"] = counts
+    return seg, cand

@@ -1,0 +1,190 @@
+// taxator-b200: command-line drop-in for `taxator -a rpa` (core/taxator.cpp) with the RPA hot path on
+// B200 GPUs.  Same inputs (alignments on stdin, FASTA (+.fai) stores, seqid->taxid mapping,
+// $TAXATORTK_TAXONOMY_NCBI) and the same GFF3 on stdout.  Record sets are gathered into batches and
+// handed to RPAPredictionModelGPU::predictBatch; output keeps the input order.
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "driver.h"
+#include "records.h"
+#include "rpa_model.h"
+#include "seqstore.h"
+#include "taxonomy.h"
+
+using namespace taxator_b200;
+
+static const char* kVersion = "1.5.0-b200";
+
+struct Options {
+  std::string algorithm = "rpa", mapping, query, query_index, ref, ref_index, logfile = "/dev/null", dataformat = "nucleotide";
+  std::vector<std::string> ranks;
+  unsigned processors = 1;
+  bool split_alignments = true, alignments_sorted = false, delete_unmarked = true;
+  float filterout = 0.5f, toppercent = 0.05f;
+  std::vector<int> gpus = {0};
+  size_t batch_segments = 200000;
+  bool timing = false;
+};
+
+static void usage(std::ostream& os) {
+  os << "Allowed options:\n"
+        "  -h [ --help ]                     show help message\n"
+        "  -V [ --version ]                  show program version\n"
+        "  -a [ --algorithm ] arg (=rpa)     only rpa is accelerated by this build\n"
+        "  -g [ --seqid-taxid-mapping ] arg  filename of seqid->taxid mapping for reference\n"
+        "  -q [ --query-sequences ] arg      query sequences FASTA\n"
+        "  -v [ --query-sequences-index ] arg  query sequences FASTA index\n"
+        "  -f [ --ref-sequences ] arg        reference sequences FASTA\n"
+        "  -i [ --ref-sequences-index ] arg  reference FASTA index (.fai)\n"
+        "  -p [ --processors ] arg (=1)      accepted for compatibility (the work runs on the GPUs)\n"
+        "  -l [ --logfile ] arg (=/dev/null) per-segment STATS log\n"
+        "  -b [ --dataformat ] arg (=nucleotide)  nucleotide or protein\n"
+        "  -r [ --ranks ] arg...             node ranks at which to do predictions\n"
+        "  -s [ --split-alignments ] arg (=1)\n"
+        "  -o [ --alignments-sorted ] arg (=0)\n"
+        "  -d [ --delete-notranks ] arg (=1)\n"
+        "  -x [ --heuristic-cutoff ] arg (=0.5)\n"
+        "  -t [ --toppercent ] arg (=0.05)\n"
+        "  --gpus arg (=0)                   comma separated CUDA device indices to shard segments over\n"
+        "  --batch-segments arg (=200000)    record sets per GPU batch\n"
+        "  --timing                          print load/predict timing to stderr\n";
+}
+
+static bool parse_bool(const std::string& s) {
+  if (s == "1" || s == "true" || s == "on" || s == "yes") return true;
+  if (s == "0" || s == "false" || s == "off" || s == "no") return false;
+  throw TaxatorError("bad boolean option value: " + s);
+}
+
+static int parse_args(int argc, char** argv, Options& o) {
+  struct Spec { const char* lng; char shrt; };
+  static const Spec specs[] = {{"help", 'h'}, {"version", 'V'}, {"algorithm", 'a'}, {"seqid-taxid-mapping", 'g'},
+    {"query-sequences", 'q'}, {"query-sequences-index", 'v'}, {"ref-sequences", 'f'}, {"ref-sequences-index", 'i'},
+    {"processors", 'p'}, {"logfile", 'l'}, {"dataformat", 'b'}, {"ranks", 'r'}, {"split-alignments", 's'},
+    {"alignments-sorted", 'o'}, {"delete-notranks", 'd'}, {"heuristic-cutoff", 'x'}, {"toppercent", 't'},
+    {"gpus", 'G'}, {"batch-segments", 'B'}, {"timing", 'T'},
+    // accepted and ignored (other models' knobs)
+    {"max-evalue", 'e'}, {"min-support", 'c'}, {"minscore", 'm'}, {"nbest", 'n'}, {"db-whitelist", 'w'},
+    {"ignore-unclassified", 'u'}, {"citation", 'C'}, {"advanced-options", 'A'}};
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    char key = 0;
+    std::string val; bool has_val = false;
+    if (a.size() > 2 && a[0] == '-' && a[1] == '-') {
+      std::string name = a.substr(2);
+      size_t eq = name.find('=');
+      if (eq != std::string::npos) { val = name.substr(eq + 1); has_val = true; name.resize(eq); }
+      for (const auto& s : specs) if (name == s.lng) key = s.shrt;
+    } else if (a.size() >= 2 && a[0] == '-') {
+      for (const auto& s : specs) if (a[1] == s.shrt && s.shrt != 'G' && s.shrt != 'B' && s.shrt != 'T' && s.shrt != 'C' && s.shrt != 'A') key = s.shrt;
+      if (a.size() > 2) { val = a.substr(2); has_val = true; }
+    }
+    if (!key) throw TaxatorError("unrecognised option '" + a + "'");
+    auto need = [&]() -> std::string {
+      if (has_val) return val;
+      if (i + 1 >= argc) throw TaxatorError("option '" + a + "' needs a value");
+      return argv[++i];
+    };
+    switch (key) {
+      case 'h': usage(std::cout); return 1;
+      case 'V': std::cout << kVersion << std::endl; return 1;
+      case 'C': case 'A': return 1;
+      case 'a': o.algorithm = need(); break;
+      case 'g': o.mapping = need(); break;
+      case 'q': o.query = need(); break;
+      case 'v': o.query_index = need(); break;
+      case 'f': o.ref = need(); break;
+      case 'i': o.ref_index = need(); break;
+      case 'p': o.processors = (unsigned)std::stoul(need()); break;
+      case 'l': o.logfile = need(); break;
+      case 'b': o.dataformat = need(); break;
+      case 'r':
+        if (has_val) o.ranks.push_back(val);
+        while (i + 1 < argc && argv[i + 1][0] != '-') o.ranks.push_back(argv[++i]);
+        break;
+      case 's': o.split_alignments = parse_bool(need()); break;
+      case 'o': o.alignments_sorted = parse_bool(need()); break;
+      case 'd': o.delete_unmarked = parse_bool(need()); break;
+      case 'x': o.filterout = std::stof(need()); break;
+      case 't': o.toppercent = std::stof(need()); break;
+      case 'G': {
+        o.gpus.clear();
+        std::stringstream ss(need());
+        std::string tok;
+        while (std::getline(ss, tok, ',')) if (!tok.empty()) o.gpus.push_back(std::stoi(tok));
+        break;
+      }
+      case 'B': o.batch_segments = std::stoul(need()); break;
+      case 'T': o.timing = true; break;
+      case 'u': break;
+      default: need(); break;  // ignored options with a value
+    }
+  }
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  Options opt;
+  try {
+    if (parse_args(argc, argv, opt)) return EXIT_SUCCESS;
+    if (opt.ranks.empty()) opt.ranks = kDefaultRanks;
+    if (opt.mapping.empty()) {
+      std::cout << "Specify a taxonomy mapping file for the reference sequence identifiers" << std::endl;
+      usage(std::cout);
+      return EXIT_FAILURE;
+    }
+    if (opt.algorithm != "rpa") {
+      std::cout << "this build accelerates only the rpa algorithm; use the reference taxator for: " << opt.algorithm << std::endl;
+      return EXIT_FAILURE;
+    }
+    if (opt.dataformat != "nucleotide" && opt.dataformat != "protein") {
+      std::cout << "data format can either be nucleotide or protein" << std::endl;
+      return EXIT_FAILURE;
+    }
+    const bool protein = opt.dataformat == "protein";
+    auto t0 = std::chrono::steady_clock::now();
+    FlatTaxonomy tax = load_taxonomy_from_environment(opt.ranks, opt.delete_unmarked);
+    SeqIdMapping mapping = load_mapping(opt.mapping);
+    std::ofstream logsink(opt.logfile.c_str(), std::ios_base::app);
+
+    SeqStore q_store;
+    if (opt.query_index.empty()) {
+      std::cerr << "Loading '" << opt.query;
+      q_store = load_fasta_inmemory(opt.query);
+      std::cerr << "' (total=" << q_store.size() << ")" << std::endl;
+    } else q_store = load_fasta_indexed(opt.query, opt.query_index);
+    // the reference store always uses index semantics (ids = first word / .fai name column); the
+    // reference's in-memory mode returns un-reversed whole sequences for reverse hits
+    // (sequencestorage.hh:122-130) and is not reproduced.
+    SeqStore db_store = load_fasta_indexed(opt.ref, opt.ref_index.empty() ? opt.ref + ".fai" : opt.ref_index);
+
+    RPAPredictionModelGPU model(&tax, q_store, db_store, opt.filterout, opt.toppercent, protein, opt.gpus);
+    auto t1 = std::chrono::steady_clock::now();
+
+    std::ios::sync_with_stdio(false);
+    RecordSetReader reader(std::cin, mapping, tax, opt.split_alignments, opt.alignments_sorted);
+    const uint64_t total_sets = run_prediction_stream(
+        reader, tax, opt.batch_segments,
+        [&](std::vector<RecordSet>& sets, std::vector<PredictionRecord>& precs, std::ostream& log) {
+          model.predictBatch(sets, precs, log);
+        },
+        std::cout, logsink);
+    auto t2 = std::chrono::steady_clock::now();
+    if (opt.timing) {
+      auto st = model.stats();
+      const double load_s = std::chrono::duration<double>(t1 - t0).count();
+      const double run_s = std::chrono::duration<double>(t2 - t1).count();
+      std::cerr << "taxator-b200: load " << load_s << " s, predict " << run_s << " s, " << total_sets << " segments, "
+                << st.alignments << " alignments, " << st.cells << " cells, " << (run_s > 0 ? st.cells / run_s / 1e9 : 0)
+                << " GCUPS" << std::endl;
+    }
+    return EXIT_SUCCESS;
+  } catch (std::exception& e) {
+    std::cerr << "An unrecoverable error occurred: " << e.what() << std::endl;
+    return EXIT_FAILURE;
+  }
+}

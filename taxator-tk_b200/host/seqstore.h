@@ -1,0 +1,30 @@
+// Host side of the sequence stores: reads FASTA (+ .fai) into the flat (chars, offset, length) table
+// that trpa_load_store() packs into HBM, and keeps the id -> ordinal map.  Mirrors
+// RandomInmemorySeqStoreRO (ids = full FASTA header, core/src/sequencestorage.hh:56-140) and
+// RandomIndexedSeqstoreRO (ids = name column of the .fai, :318-406, core/src/faidx.h:438-524).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace taxator_b200 {
+
+struct SeqStore {
+  std::string chars;               // residues of all sequences, concatenated, no line breaks
+  std::vector<uint64_t> off;
+  std::vector<uint32_t> len;
+  std::vector<std::string> ids;
+  std::unordered_map<std::string, uint32_t> index;
+
+  uint32_t ordinal(const std::string& id) const;  // throws SequenceNotFound
+  size_t size() const { return len.size(); }
+};
+
+// whole FASTA in memory; id = complete header line after '>'
+SeqStore load_fasta_inmemory(const std::string& fasta);
+// FASTA + samtools-style .fai (name, length, offset, linebases, linebytes); id = .fai name column.
+// A missing .fai is built in memory (name = header up to the first whitespace, faidx.h:590).
+SeqStore load_fasta_indexed(const std::string& fasta, const std::string& fai);
+
+}  // namespace taxator_b200

@@ -59,7 +59,7 @@ WORKLOADS = {
 
 # ALU-pipe instructions per 32-cell word-step of the W=20 edit-distance kernel, counted in SASS
 # (profiles/r01_sass_mix.md): LOP3 + IADD3.X + SHF per word plus the per-column boundary work.
-ALU_OPS_PER_WORDSTEP = 13.9
+ALU_OPS_PER_WORDSTEP = 13.3
 
 
 def make_data(workload, seed, n_queries=None):

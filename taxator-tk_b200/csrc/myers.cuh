@@ -27,7 +27,6 @@ namespace trpa {
 template <int N>
 struct AddChain;
 
-#define TRPA_ADDC_HEAD "{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %0, %1;\n\t"
 template <>
 struct AddChain<1> {
   static __device__ __forceinline__ u32 run(u32* s, const u32* a, const u32* b, u32 cin, u32 K) {
@@ -91,8 +90,6 @@ __device__ __forceinline__ u32 add_words(u32 (&s)[W], const u32 (&a)[W], const u
   u32 K = 0x80000000u;
 #pragma unroll
   for (int w0 = 0; w0 < W; w0 += 4) {
-    constexpr int dummy = 0;
-    (void)dummy;
     if (W - w0 >= 4) c = AddChain<4>::run(&s[w0], &a[w0], &b[w0], c, K);
     else if (W - w0 == 3) c = AddChain<3>::run(&s[w0], &a[w0], &b[w0], c, K);
     else if (W - w0 == 2) c = AddChain<2>::run(&s[w0], &a[w0], &b[w0], c, K);

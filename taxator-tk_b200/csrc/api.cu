@@ -96,7 +96,7 @@ struct trpa_ctx {
   DevBuf<PairDesc> d_pairs, d_pairs_sorted;
   DevBuf<StageReq> d_stage;
   DevBuf<u32> d_counters;
-  DevBuf<u32> d_hist;         // kNumShapes counts + kNumShapes cursors
+  DevBuf<u32> d_hist;         // kNumShapes counts + scatter cursors + kernel work cursors
   DevBuf<uint2> d_buckets;    // kNumShapes {start,count}
   DevBuf<uint2> arena_planes;
   DevBuf<u32> arena_n;
@@ -209,6 +209,8 @@ static Taxonomy dev_tax(trpa_ctx* c) { return Taxonomy{c->t_parent.p, c->t_left.
 static int launch_myers_buckets(trpa_ctx* c, const u32* geom_counts, const PairDesc* sorted, const SeqDesc* descs,
                                 const uint2* planes, const u32* nplane, int* out, u32 max_len) {
   const u32 stride = (max_len + 31) / 32 + 1;
+  // work cursors of the persistent kernels (one per shape)
+  CK(cudaMemsetAsync(c->d_hist.p + 2 * kNumShapes, 0, sizeof(u32) * kNumShapes, c->stream));
   for (int g = 0; g < kNumW * kNumL; ++g) {
     const u32 cnt = geom_counts[g];
     if (!cnt) continue;
@@ -216,12 +218,13 @@ static int launch_myers_buckets(trpa_ctx* c, const u32* geom_counts, const PairD
     const int W = shape_W(shape_widx(g));
     u32* scr = nullptr;
     if (L == 32 && (u64)stride * 32 > (u64)32 * W * 32) {  // some pattern may need >1 strip
-      if (c->scratch.ensure((size_t)cnt * 3 * stride)) return TRPA_ERR_NOMEM;
+      if (c->scratch.ensure((size_t)myers_group_slots(g, cnt) * 3 * stride)) return TRPA_ERR_NOMEM;
       scr = c->scratch.p;
     }
     for (int hasn = 0; hasn < 2; ++hasn) {
       const int shape = g + hasn * kNumW * kNumL;
-      CK(launch_myers(shape, sorted, cnt, descs, planes, nplane, out, scr, stride, c->d_buckets.p + shape, c->stream));
+      CK(launch_myers(shape, sorted, cnt, descs, planes, nplane, out, scr, stride, c->d_buckets.p + shape,
+                      c->d_hist.p + 2 * kNumShapes + shape, c->stream));
       c->prof.launches_edit_distance++;
     }
   }
@@ -442,7 +445,7 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
       c->d_bf_d.ensure(nslots + 1) || c->d_bf_node.ensure(nslots + 1) || c->d_cflags.ensure(n_cands + 1) ||
       c->d_og_i.ensure(n_cands + 1) || c->d_og_d.ensure(n_cands + 1) || c->d_res.ensure(2 * nslots + 2) ||
       c->d_descs.ensure(nslots + 1) || c->d_pairs.ensure(nslots + 1) || c->d_pairs_sorted.ensure(nslots + 1) ||
-      c->d_stage.ensure(nslots + 1) || c->d_counters.ensure(kNumCounters) || c->d_hist.ensure(2 * kNumShapes) ||
+      c->d_stage.ensure(nslots + 1) || c->d_counters.ensure(kNumCounters) || c->d_hist.ensure(3 * kNumShapes) ||
       c->d_buckets.ensure(kNumShapes))
     return TRPA_ERR_NOMEM;
   if (protein) { if (c->arena_aa.ensure(units_cap + 16)) return TRPA_ERR_NOMEM; }
@@ -529,7 +532,7 @@ int trpa_batch_run(trpa_ctx* c) {
         c->prof.launches_protein++;
       } else {
         ev = begin_event(c, EV_OTHER);
-        CK(cudaMemsetAsync(c->d_hist.p, 0, sizeof(u32) * 2 * kNumShapes, c->stream));
+        CK(cudaMemsetAsync(c->d_hist.p, 0, sizeof(u32) * 3 * kNumShapes, c->stream));
         const u32 blocks = std::min<u32>((n_pairs + 255) / 256, 148 * 8);
         classify_kernel<<<blocks, 256, 0, c->stream>>>(c->d_pairs.p, c->d_counters.p, c->d_descs.p, c->d_hist.p);
         scan_kernel<<<1, 32, 0, c->stream>>>(c->d_hist.p, c->d_buckets.p);
@@ -600,7 +603,7 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   DevBuf<SeqDesc> d_sd; DevBuf<uint2> planes; DevBuf<u32> nplane; DevBuf<PairDesc> d_pairs, d_sorted; DevBuf<int32_t> d_out;
   DevBuf<u32> d_cnt;
   if (d_sd.ensure(n_seq + 1) || planes.ensure(words + 2) || nplane.ensure(words + 2) || d_pairs.ensure(n_pairs) ||
-      d_sorted.ensure(n_pairs) || d_out.ensure(n_pairs) || d_cnt.ensure(kNumCounters) || c->d_hist.ensure(2 * kNumShapes) ||
+      d_sorted.ensure(n_pairs) || d_out.ensure(n_pairs) || d_cnt.ensure(kNumCounters) || c->d_hist.ensure(3 * kNumShapes) ||
       c->d_buckets.ensure(kNumShapes))
     return TRPA_ERR_NOMEM;
   CK(cudaMemcpyAsync(d_sd.p, sd.data(), sizeof(SeqDesc) * n_seq, cudaMemcpyHostToDevice, c->stream));
@@ -627,7 +630,7 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   cnt[CN_PAIRS] = n_pairs;
   CK(cudaMemcpyAsync(d_pairs.p, hp.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(d_cnt.p, cnt.data(), sizeof(u32) * kNumCounters, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemsetAsync(c->d_hist.p, 0, sizeof(u32) * 2 * kNumShapes, c->stream));
+  CK(cudaMemsetAsync(c->d_hist.p, 0, sizeof(u32) * 3 * kNumShapes, c->stream));
   const u32 blocks = std::min<u32>((n_pairs + 255) / 256, 148 * 8);
   classify_kernel<<<blocks, 256, 0, c->stream>>>(d_pairs.p, d_cnt.p, d_sd.p, c->d_hist.p);
   scan_kernel<<<1, 32, 0, c->stream>>>(c->d_hist.p, c->d_buckets.p);

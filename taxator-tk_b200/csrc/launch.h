@@ -6,9 +6,11 @@ namespace trpa {
 
 // edit distance: pairs[0..count) all of one shape (shapes.h); scratch only for multi-strip pairs
 // bucket (nullable): device {start,count} of the shape inside pairs; count is then the grid bound
+// cursor: zeroed device counter of this launch (persistent kernel work fetch)
 cudaError_t launch_myers(int shape, const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint2* planes,
                          const u32* nplane, int* out, u32* scratch, u32 scratch_stride, const uint2* bucket,
-                         cudaStream_t stream);
+                         u32* cursor, cudaStream_t stream);
+u32 myers_group_slots(int shape, u32 count);
 
 // BLOSUM62 linear-gap NW with traced length; out2[pair.out] = {mutual, #diagonal steps}
 // scratch: scratch_stride int2 per pair, needed only when a pair's A is longer than 512 residues

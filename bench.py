@@ -58,8 +58,8 @@ WORKLOADS = {
 }
 
 # ALU-pipe instructions per 32-cell word-step of the W=20 edit-distance kernel, counted in SASS
-# (profiles/r01_sass_mix.md): LOP3 + IADD3.X + SHF per word plus the per-column boundary work.
-ALU_OPS_PER_WORDSTEP = 13.3
+# (profiles/r01_sass_mix.md, myers2_kernel<20,false>): 7.1 LOP3 + 2.2 SHF + 1.03 IADD3.X + 0.1 other.
+ALU_OPS_PER_WORDSTEP = 10.4
 
 
 def make_data(workload, seed, n_queries=None):

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -28,6 +29,23 @@ int alu_probe_ops_per_iter();
       return TRPA_ERR_CUDA;                                                             \
     }                                                                                   \
   } while (0)
+
+// host-side parallel loop over [0, n) in contiguous blocks (batch preparation is memory bound and
+// would otherwise cost more than the H2D copy of a 5 M-candidate batch)
+template <class F>
+static void parallel_blocks(size_t n, const F& f) {
+  unsigned T = std::thread::hardware_concurrency();
+  if (T > 16) T = 16;
+  if (T < 2 || n < 4096) { f(0, n); return; }
+  std::vector<std::thread> th;
+  const size_t per = (n + T - 1) / T;
+  for (unsigned t = 0; t < T; ++t) {
+    const size_t b = t * per, e = std::min(n, b + per);
+    if (b >= e) break;
+    th.emplace_back([&f, b, e]() { f(b, e); });
+  }
+  for (auto& x : th) x.join();
+}
 
 template <class T>
 struct DevBuf {
@@ -104,7 +122,8 @@ struct trpa_ctx {
   u64 arena_units = 0;
   DevBuf<u32> scratch;
   DevBuf<int2> scratch_aa;
-  u32* h_counters = nullptr;  // pinned
+  u32* h_counters = nullptr;  // pinned: kNumCounters round counters + kNumShapes shape histogram
+  int num_sms = 148;
   // profiling
   trpa_profile prof;
   std::vector<EventPair> ev_pool;
@@ -129,13 +148,12 @@ __global__ void init_state_kernel(SegState* st, u32 n) {
 }
 
 // exact shape of every pair of the round (needs the staged N flags) + histogram
-__global__ void classify_kernel(PairDesc* pairs, const u32* counters, const SeqDesc* descs, u32* hist) {
-  const u32 n = counters[CN_PAIRS];
+__global__ void classify_kernel(PairDesc* pairs, u32 n, const SeqDesc* descs, u32* hist, int lmin) {
   for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     PairDesc p = pairs[k];
     const SeqDesc a = descs[p.a], b = descs[p.b];
     const u32 m = a.len < b.len ? a.len : b.len;
-    const int shape = choose_shape((m + 31u) >> 5, (a.flags | b.flags) & 1u);
+    const int shape = choose_shape((m + 31u) >> 5, (a.flags | b.flags) & 1u, lmin);
     pairs[k].pad = (u32)shape;
     atomicAdd(&hist[shape], 1u);
   }
@@ -151,8 +169,7 @@ __global__ void scan_kernel(u32* hist, uint2* buckets) {
     }
   }
 }
-__global__ void scatter_kernel(const PairDesc* pairs, const u32* counters, u32* hist, PairDesc* sorted) {
-  const u32 n = counters[CN_PAIRS];
+__global__ void scatter_kernel(const PairDesc* pairs, u32 n, u32* hist, PairDesc* sorted) {
   for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const PairDesc p = pairs[k];
     const u32 pos = atomicAdd(&hist[kNumShapes + p.pad], 1u);
@@ -203,30 +220,45 @@ static int use_device(trpa_ctx* c) {
 
 static Taxonomy dev_tax(trpa_ctx* c) { return Taxonomy{c->t_parent.p, c->t_left.p, c->t_right.p, c->t_depth.p, c->root}; }
 
-// Shared by the pipeline and the low-level API: run the edit-distance kernels over `n_pairs` pairs
-// whose exact shapes have already been bucketed on the device (d_buckets), given host-side upper
-// bounds per geometry.
-static int launch_myers_buckets(trpa_ctx* c, const u32* geom_counts, const PairDesc* sorted, const SeqDesc* descs,
-                                const uint2* planes, const u32* nplane, int* out, u32 max_len) {
+// Shared by the pipeline and the low-level API.
+// bucket_pairs: exact kernel shape of every pair (length class, has-N, and -- when the round is too
+// small to fill the GPU -- more lanes per pair), counting sort by shape on the device; the per-shape
+// counts come back to the host (h_hist) so that only non-empty shapes are launched.
+static int bucket_pairs(trpa_ctx* c, PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, PairDesc* sorted, u32* h_hist) {
+  CK(cudaMemsetAsync(c->d_hist.p, 0, sizeof(u32) * 3 * kNumShapes, c->stream));
+  const u32 blocks = std::min<u32>((n_pairs + 255) / 256, 148 * 8);
+  const int lmin = lmin_for(n_pairs, (u32)c->num_sms * 16u * 32u);
+  classify_kernel<<<blocks, 256, 0, c->stream>>>(pairs, n_pairs, descs, c->d_hist.p, lmin);
+  scan_kernel<<<1, 32, 0, c->stream>>>(c->d_hist.p, c->d_buckets.p);
+  scatter_kernel<<<blocks, 256, 0, c->stream>>>(pairs, n_pairs, c->d_hist.p, sorted);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h_hist, c->d_hist.p, sizeof(u32) * kNumShapes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// one launch per non-empty shape over the shape-sorted pair list
+static int launch_myers_shapes(trpa_ctx* c, const u32* h_hist, const PairDesc* sorted, const SeqDesc* descs,
+                               const uint2* planes, const u32* nplane, int* out, u32 max_len) {
   const u32 stride = (max_len + 31) / 32 + 1;
   // work cursors of the persistent kernels (one per shape)
   CK(cudaMemsetAsync(c->d_hist.p + 2 * kNumShapes, 0, sizeof(u32) * kNumShapes, c->stream));
-  for (int g = 0; g < kNumW * kNumL; ++g) {
-    const u32 cnt = geom_counts[g];
+  u32 start = 0;
+  for (int shape = 0; shape < kNumShapes; ++shape) {
+    const u32 cnt = h_hist[shape];
     if (!cnt) continue;
-    const int L = 1 << shape_lidx(g);
-    const int W = shape_W(shape_widx(g));
+    const int L = 1 << shape_lidx(shape);
+    const int W = shape_W(shape_widx(shape));
     u32* scr = nullptr;
     if (L == 32 && (u64)stride * 32 > (u64)32 * W * 32) {  // some pattern may need >1 strip
-      if (c->scratch.ensure((size_t)myers_group_slots(g, cnt) * 3 * stride)) return TRPA_ERR_NOMEM;
+      // kernels of one stream run back to back, so one scratch area serves all shapes
+      if (c->scratch.ensure((size_t)myers_group_slots(shape, cnt) * 3 * stride)) return TRPA_ERR_NOMEM;
       scr = c->scratch.p;
     }
-    for (int hasn = 0; hasn < 2; ++hasn) {
-      const int shape = g + hasn * kNumW * kNumL;
-      CK(launch_myers(shape, sorted, cnt, descs, planes, nplane, out, scr, stride, c->d_buckets.p + shape,
-                      c->d_hist.p + 2 * kNumShapes + shape, c->stream));
-      c->prof.launches_edit_distance++;
-    }
+    CK(launch_myers(shape, sorted + start, cnt, descs, planes, nplane, out, scr, stride, nullptr,
+                    c->d_hist.p + 2 * kNumShapes + shape, c->stream));
+    c->prof.launches_edit_distance++;
+    start += cnt;
   }
   return 0;
 }
@@ -258,6 +290,7 @@ trpa_ctx* trpa_create(int device, void* cuda_stream) {
     c->own_stream = true;
   }
   if (cudaMallocHost(&c->h_counters, sizeof(u32) * (kNumCounters + 2 * kNumShapes)) != cudaSuccess) { set_error("cudaMallocHost failed"); delete c; return nullptr; }
+  if (cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->num_sms <= 0) c->num_sms = 148;
   return c;
 }
 
@@ -378,26 +411,58 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
     if ((u64)segs[s].cand_begin + segs[s].cand_count > n_cands) { set_error("segment candidate range out of bounds"); return TRPA_ERR_ARG; }
     if (segs[s].cand_count && segs[s].query_seq >= Q.n_seq) { set_error("segment query ordinal out of range"); return TRPA_ERR_ARG; }
   }
-  for (u32 k = 0; k < n_cands; ++k) {
-    if (cands[k].ref_seq >= R.n_seq) { set_error("candidate reference ordinal out of range"); return TRPA_ERR_ARG; }
-    if (cands[k].node >= c->n_nodes) { set_error("candidate taxon node out of range"); return TRPA_ERR_ARG; }
-    if (cands[k].qstart > cands[k].qstop || cands[k].qstart == 0) { set_error("candidate query range invalid (qstart must be >= 1 and <= qstop)"); return TRPA_ERR_ARG; }
-    if (cands[k].rstart == 0 || cands[k].rstop == 0) { set_error("candidate reference coordinates are 1-based"); return TRPA_ERR_ARG; }
+  {
+    std::vector<int> bad(17, 0);
+    const u32 nseq = R.n_seq, nnodes = c->n_nodes;
+    parallel_blocks(n_cands, [&](size_t b, size_t e) {
+      int code = 0;
+      for (size_t k = b; k < e && !code; ++k) {
+        if (cands[k].ref_seq >= nseq) code = 1;
+        else if (cands[k].node >= nnodes) code = 2;
+        else if (cands[k].qstart > cands[k].qstop || cands[k].qstart == 0) code = 3;
+        else if (cands[k].rstart == 0 || cands[k].rstop == 0) code = 4;
+      }
+      if (code) bad[code] = 1;
+    });
+    if (bad[1]) { set_error("candidate reference ordinal out of range"); return TRPA_ERR_ARG; }
+    if (bad[2]) { set_error("candidate taxon node out of range"); return TRPA_ERR_ARG; }
+    if (bad[3]) { set_error("candidate query range invalid (qstart must be >= 1 and <= qstop)"); return TRPA_ERR_ARG; }
+    if (bad[4]) { set_error("candidate reference coordinates are 1-based"); return TRPA_ERR_ARG; }
   }
   // A segment whose best score is below (1-t)*best (i.e. negative) realigns nothing in pass 0 and
   // trips assert(!qgroup.empty()) in the reference (hh:563); reject it instead of guessing.
+  c->h_segs.assign(segs, segs + n_segs);
+  c->h_cands.resize(n_cands);
+  std::vector<u64> bound(n_segs);
+  std::vector<u32> maxspan(n_segs, 0);
   {
     const float factor = 1. - c->toppercent;
-    for (u32 s = 0; s < n_segs; ++s) {
-      if (segs[s].cand_count < 2) continue;
-      float best = cands[segs[s].cand_begin].score;
-      for (u32 k = 1; k < segs[s].cand_count; ++k) best = std::max(best, cands[segs[s].cand_begin + k].score);
-      if (!(best >= factor * best)) { set_error("segment with negative best alignment score: undefined in the reference (hh:563)"); return TRPA_ERR_ARG; }
-    }
+    int neg = 0;
+    trpa_candidate* hc = c->h_cands.data();
+    const trpa_segment* hs = c->h_segs.data();
+    parallel_blocks(n_segs, [&](size_t b, size_t e) {
+      for (size_t s = b; s < e; ++s) {
+        const trpa_segment sg = hs[s];
+        trpa_candidate* dst = hc + sg.cand_begin;
+        std::copy(cands + sg.cand_begin, cands + sg.cand_begin + sg.cand_count, dst);
+        if (sg.cand_count >= 2) {
+          float best = dst[0].score;
+          for (u32 k = 1; k < sg.cand_count; ++k) best = std::max(best, dst[k].score);
+          if (!(best >= factor * best)) neg = 1;
+        }
+        sort_candidates(&sg, 1, hc);
+        bound[s] = segment_arena_bound(sg, hc, protein);
+        u32 ms = 0;
+        for (u32 k = 0; k < sg.cand_count; ++k) {
+          const trpa_candidate& x = dst[k];
+          const u64 span = (x.rstart <= x.rstop ? (u64)x.rstop - x.rstart : (u64)x.rstart - x.rstop) + 1;
+          ms = (u32)std::min<u64>(0xffffffffull, std::max<u64>(ms, span));
+        }
+        maxspan[s] = ms;
+      }
+    });
+    if (neg) { set_error("segment with negative best alignment score: undefined in the reference (hh:563)"); return TRPA_ERR_ARG; }
   }
-  c->h_segs.assign(segs, segs + n_segs);
-  c->h_cands.assign(cands, cands + n_cands);
-  sort_candidates(c->h_segs.data(), n_segs, c->h_cands.data());
   c->n_segs = n_segs; c->n_cands = n_cands;
 
   // arena + chunk plan
@@ -412,17 +477,11 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
   }
   const u64 unit_bytes = protein ? 1 : 12;
   u64 units_cap = std::min<u64>(arena_bytes / unit_bytes, 0xfffffff0ull);
-  std::vector<u64> bound(n_segs);
   u64 total_bound = 0, max_bound = 0; u32 max_len = 0;
   for (u32 s = 0; s < n_segs; ++s) {
-    bound[s] = segment_arena_bound(c->h_segs[s], c->h_cands.data(), protein);
     total_bound += bound[s];
     max_bound = std::max(max_bound, bound[s]);
-  }
-  for (u32 k = 0; k < n_cands; ++k) {
-    const trpa_candidate& x = c->h_cands[k];
-    const u64 span = (x.rstart <= x.rstop ? (u64)x.rstop - x.rstart : (u64)x.rstart - x.rstop) + 1;
-    max_len = (u32)std::min<u64>(0xffffffffull, std::max<u64>(max_len, span));
+    max_len = std::max(max_len, maxspan[s]);
   }
   // extensions can add at most the query range; sequences are clipped to the store anyway
   max_len = std::min<u64>((u64)max_len + Q.max_len, std::max(R.max_len, Q.max_len));
@@ -532,23 +591,19 @@ int trpa_batch_run(trpa_ctx* c) {
         c->prof.launches_protein++;
       } else {
         ev = begin_event(c, EV_OTHER);
-        CK(cudaMemsetAsync(c->d_hist.p, 0, sizeof(u32) * 3 * kNumShapes, c->stream));
-        const u32 blocks = std::min<u32>((n_pairs + 255) / 256, 148 * 8);
-        classify_kernel<<<blocks, 256, 0, c->stream>>>(c->d_pairs.p, c->d_counters.p, c->d_descs.p, c->d_hist.p);
-        scan_kernel<<<1, 32, 0, c->stream>>>(c->d_hist.p, c->d_buckets.p);
-        scatter_kernel<<<blocks, 256, 0, c->stream>>>(c->d_pairs.p, c->d_counters.p, c->d_hist.p, c->d_pairs_sorted.p);
-        CK(cudaGetLastError());
+        u32* h_hist = c->h_counters + kNumCounters;
+        int rc = bucket_pairs(c, c->d_pairs.p, n_pairs, c->d_descs.p, c->d_pairs_sorted.p, h_hist);
+        if (rc) return rc;
         end_event(c, ev);
         c->prof.launches_other += 3;
         ev = begin_event(c, EV_MYERS);
-        int rc = launch_myers_buckets(c, c->h_counters + CN_GEOM0, c->d_pairs_sorted.p, c->d_descs.p, c->arena_planes.p,
-                                      c->arena_n.p, c->d_res.p, c->max_stage_len);
+        rc = launch_myers_shapes(c, h_hist, c->d_pairs_sorted.p, c->d_descs.p, c->arena_planes.p, c->arena_n.p,
+                                 c->d_res.p, c->max_stage_len);
         if (rc) return rc;
         end_event(c, ev);
       }
       // reset the per-round counters, keep the arena cursor
       CK(cudaMemsetAsync(c->d_counters.p + CN_PAIRS, 0, sizeof(u32) * 3, c->stream));
-      CK(cudaMemsetAsync(c->d_counters.p + CN_GEOM0, 0, sizeof(u32) * kNumW * kNumL, c->stream));
     }
   }
   // totals for the profile
@@ -620,33 +675,23 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   for (u32 i = 0; i < n_seq; ++i) sd[i].flags = h_flags[i];
   CK(cudaMemcpyAsync(d_sd.p, sd.data(), sizeof(SeqDesc) * n_seq, cudaMemcpyHostToDevice, c->stream));
   std::vector<PairDesc> hp(n_pairs);
-  std::vector<u32> geom(kNumW * kNumL, 0);
-  for (u32 k = 0; k < n_pairs; ++k) {
-    hp[k] = PairDesc{pair_a[k], pair_b[k], k, 0};
-    const u32 m = std::min(len[pair_a[k]], len[pair_b[k]]);
-    geom[choose_shape((m + 31) / 32, 0)]++;
-  }
-  std::vector<u32> cnt(kNumCounters, 0);
-  cnt[CN_PAIRS] = n_pairs;
+  for (u32 k = 0; k < n_pairs; ++k) hp[k] = PairDesc{pair_a[k], pair_b[k], k, 0};
   CK(cudaMemcpyAsync(d_pairs.p, hp.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(d_cnt.p, cnt.data(), sizeof(u32) * kNumCounters, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemsetAsync(c->d_hist.p, 0, sizeof(u32) * 3 * kNumShapes, c->stream));
-  const u32 blocks = std::min<u32>((n_pairs + 255) / 256, 148 * 8);
-  classify_kernel<<<blocks, 256, 0, c->stream>>>(d_pairs.p, d_cnt.p, d_sd.p, c->d_hist.p);
-  scan_kernel<<<1, 32, 0, c->stream>>>(c->d_hist.p, c->d_buckets.p);
-  scatter_kernel<<<blocks, 256, 0, c->stream>>>(d_pairs.p, d_cnt.p, c->d_hist.p, d_sorted.p);
-  CK(cudaGetLastError());
+  std::vector<u32> h_hist(kNumShapes, 0);
+  rc = bucket_pairs(c, d_pairs.p, n_pairs, d_sd.p, d_sorted.p, c->h_counters + kNumCounters);
+  if (rc) return rc;
+  memcpy(h_hist.data(), c->h_counters + kNumCounters, sizeof(u32) * kNumShapes);
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   if (repeat < 1) repeat = 1;
   // one untimed pass when timing is requested
   if (kernel_ms && repeat > 1) {
-    rc = launch_myers_buckets(c, geom.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
+    rc = launch_myers_shapes(c, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
     if (rc) return rc;
   }
   CK(cudaEventRecord(e0, c->stream));
   for (int r = 0; r < repeat; ++r) {
-    rc = launch_myers_buckets(c, geom.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
+    rc = launch_myers_shapes(c, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
     if (rc) return rc;
   }
   CK(cudaEventRecord(e1, c->stream));

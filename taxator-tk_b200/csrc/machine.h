@@ -72,8 +72,8 @@ struct Taxonomy {
 };
 
 // Work queues of one round (device memory); counters[] is what the host reads back.
-enum Counter : uint32_t { CN_PAIRS = 0, CN_STAGE, CN_ACTIVE, CN_ARENA, CN_OVERFLOW, CN_GEOM0 /* + kNumW*kNumL */ };
-constexpr uint32_t kNumCounters = CN_GEOM0 + kNumW * kNumL;
+enum Counter : uint32_t { CN_PAIRS = 0, CN_STAGE, CN_ACTIVE, CN_ARENA, CN_OVERFLOW, CN_END };
+constexpr uint32_t kNumCounters = 8;
 
 struct Batch {
   // inputs
@@ -161,11 +161,6 @@ struct Machine {
     S.cells += (uint64_t)la * lb;
     const uint32_t q = TRPA_ATOMIC_ADD_U32(&B.counters[CN_PAIRS], 1u);
     B.pairs[q] = PairDesc{da, db, slot, 0u};
-    if (!B.protein) {
-      const uint32_t m = la < lb ? la : lb;
-      const int geom = choose_shape((m + 31u) >> 5, 0);
-      TRPA_ATOMIC_ADD_U32(&B.counters[CN_GEOM0 + geom], 1u);
-    }
   }
   TRPA_HD uint32_t desc_cand(uint32_t i) const { return B.n_segs + S.cbeg + i; }
 

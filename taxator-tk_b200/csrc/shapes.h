@@ -36,11 +36,13 @@ TRPA_HD int shape_hasn(int id) { return id / (kNumW * kNumL); }
 // Cheapest padded capacity L*W >= mwords under cost = cap * (W+1)/W (the +1 models the per-column
 // boundary/broadcast work that is amortised over the W words of a lane); patterns beyond 32*24
 // words run in strips on a full warp.
-TRPA_HD int choose_shape(uint32_t mwords, int hasn) {
+// lmin_idx > 0 forces at least 2^lmin_idx lanes per pair: used when a round has too few pairs to fill
+// the GPU, where more lanes per pair shorten the critical path (latency) at the price of padding.
+TRPA_HD int choose_shape(uint32_t mwords, int hasn, int lmin_idx = 0) {
   if (mwords == 0) mwords = 1;
   int best_w = -1, best_l = -1;
   uint64_t best_cost = ~0ull;
-  for (int l = 0; l < kNumL; ++l) {
+  for (int l = lmin_idx; l < kNumL; ++l) {
     for (int w = 0; w < kNumW; ++w) {
       const uint32_t W = (uint32_t)shape_W(w);
       const uint64_t cap = (uint64_t)W << l;
@@ -58,6 +60,15 @@ TRPA_HD int choose_shape(uint32_t mwords, int hasn) {
     if (cost < best_cost || (cost == best_cost && w > best_w)) { best_cost = cost; best_w = w; }
   }
   return shape_id(best_w, kNumL - 1, hasn);
+}
+
+// Minimum lanes per pair (as log2) so that n_pairs pairs still run concurrently on `lanes` lanes.
+TRPA_HD int lmin_for(uint32_t n_pairs, uint32_t lanes) {
+  if (n_pairs == 0) return 0;
+  uint32_t per = lanes / n_pairs;
+  int l = 0;
+  while (l + 1 < kNumL && (2u << l) <= per) ++l;
+  return l;
 }
 
 }  // namespace trpa

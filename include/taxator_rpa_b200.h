@@ -108,6 +108,10 @@ void trpa_destroy(trpa_ctx* ctx);
 int trpa_set_params(trpa_ctx* ctx, float exclude_factor, float toppercent);
 /* upper bound for the per-chunk staging arena in bytes (default: 1/4 of free HBM) */
 int trpa_set_arena_bytes(trpa_ctx* ctx, uint64_t bytes);
+/* look-ahead budget for passes 1/2 (extra alignments a segment may request per round to shorten the
+ * chain of dependent rounds; results are identical for every value).  -1 (default): automatic, only
+ * when the GPU has idle capacity; 0: off. */
+int trpa_set_lookahead(trpa_ctx* ctx, int k);
 int trpa_profile_reset(trpa_ctx* ctx);
 int trpa_profile_get(trpa_ctx* ctx, trpa_profile* out);
 

@@ -107,7 +107,8 @@ struct trpa_ctx {
   DevBuf<SegState> d_state;
   DevBuf<float> d_qd, d_qsim, d_bf_d;
   DevBuf<uint8_t> d_cflags;
-  DevBuf<u32> d_og_i, d_bf_node;
+  DevBuf<u32> d_og_i, d_bf_node, d_tag;
+  int lookahead = -1;         // -1: automatic (fill idle capacity), >= 0: fixed budget
   DevBuf<int32_t> d_og_d;
   DevBuf<int32_t> d_res;      // NT: 1 int per slot; AA: 2 ints per slot
   DevBuf<SeqDesc> d_descs;
@@ -301,7 +302,7 @@ void trpa_destroy(trpa_ctx* c) {
   c->t_parent.release(); c->t_left.release(); c->t_right.release(); c->t_depth.release();
   c->store[0].release(); c->store[1].release();
   c->d_segs.release(); c->d_cands.release(); c->d_results.release(); c->d_state.release();
-  c->d_qd.release(); c->d_qsim.release(); c->d_bf_d.release(); c->d_cflags.release(); c->d_og_i.release();
+  c->d_qd.release(); c->d_qsim.release(); c->d_bf_d.release(); c->d_cflags.release(); c->d_og_i.release(); c->d_tag.release();
   c->d_bf_node.release(); c->d_og_d.release(); c->d_res.release(); c->d_descs.release(); c->d_pairs.release();
   c->d_pairs_sorted.release(); c->d_stage.release(); c->d_counters.release(); c->d_hist.release();
   c->d_buckets.release(); c->arena_planes.release(); c->arena_n.release(); c->arena_aa.release();
@@ -320,6 +321,11 @@ int trpa_set_params(trpa_ctx* c, float exclude_factor, float toppercent) {
 int trpa_set_arena_bytes(trpa_ctx* c, uint64_t bytes) {
   if (!c) { set_error("null ctx"); return TRPA_ERR_ARG; }
   c->arena_bytes = bytes;
+  return 0;
+}
+int trpa_set_lookahead(trpa_ctx* c, int k) {
+  if (!c) { set_error("null ctx"); return TRPA_ERR_ARG; }
+  c->lookahead = k < 0 ? -1 : k;
   return 0;
 }
 int trpa_profile_reset(trpa_ctx* c) { if (!c) return TRPA_ERR_ARG; memset(&c->prof, 0, sizeof(c->prof)); return 0; }
@@ -502,7 +508,7 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
   if (c->d_segs.ensure(n_segs + 1) || c->d_cands.ensure(n_cands + 1) || c->d_results.ensure(n_segs + 1) ||
       c->d_state.ensure(n_segs + 1) || c->d_qd.ensure(n_cands + 1) || c->d_qsim.ensure(n_cands + 1) ||
       c->d_bf_d.ensure(nslots + 1) || c->d_bf_node.ensure(nslots + 1) || c->d_cflags.ensure(n_cands + 1) ||
-      c->d_og_i.ensure(n_cands + 1) || c->d_og_d.ensure(n_cands + 1) || c->d_res.ensure(2 * nslots + 2) ||
+      c->d_og_i.ensure(n_cands + 1) || c->d_tag.ensure(n_cands + 1) || c->d_og_d.ensure(n_cands + 1) || c->d_res.ensure(2 * nslots + 2) ||
       c->d_descs.ensure(nslots + 1) || c->d_pairs.ensure(nslots + 1) || c->d_pairs_sorted.ensure(nslots + 1) ||
       c->d_stage.ensure(nslots + 1) || c->d_counters.ensure(kNumCounters) || c->d_hist.ensure(3 * kNumShapes) ||
       c->d_buckets.ensure(kNumShapes))
@@ -534,6 +540,7 @@ int trpa_batch_run(trpa_ctx* c) {
   B.exclude_factor = c->exclude_factor;
   B.reeval_bandwidth_factor = 1. - c->toppercent;  // taxonpredictionmodelsequence.hh:334
   B.st = c->d_state.p; B.qd = c->d_qd.p; B.qsim = c->d_qsim.p; B.cflags = c->d_cflags.p;
+  B.tag = c->d_tag.p; B.spec_k = 0;
   B.og_i = c->d_og_i.p; B.og_d = c->d_og_d.p; B.bf_d = c->d_bf_d.p; B.bf_node = c->d_bf_node.p;
   B.res_nt = c->d_res.p; B.res_aa = c->d_res.p;
   B.descs = c->d_descs.p; B.arena_capacity = (u32)c->arena_units;
@@ -557,6 +564,13 @@ int trpa_batch_run(trpa_ctx* c) {
       CK(cudaStreamSynchronize(c->stream));
       harvest_events(c);
       const u32 n_pairs = c->h_counters[CN_PAIRS], n_stage = c->h_counters[CN_STAGE], n_active = c->h_counters[CN_ACTIVE];
+      // look-ahead budget of the NEXT decide round: only as much as the GPU has idle lanes for
+      // (about 16 resident warps per SM, one pair per warp when pairs are scarce)
+      if (c->lookahead >= 0) B.spec_k = (u32)c->lookahead;
+      else {
+        const u32 cap = (u32)c->num_sms * 16u;
+        B.spec_k = n_active ? std::min<u32>(16u, cap / n_active > 0 ? cap / n_active - 1 : 0) : 0;
+      }
       if (c->h_counters[CN_OVERFLOW]) { set_error("internal: staging arena overflow"); return TRPA_ERR_STATE; }
       if (n_pairs == 0) {
         if (n_active) { set_error("internal: segments active without pending alignments"); return TRPA_ERR_STATE; }

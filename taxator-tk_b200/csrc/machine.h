@@ -91,6 +91,8 @@ struct Batch {
   float* qd;
   float* qsim;
   uint8_t* cflags;
+  uint32_t* tag;     // per candidate: anchor index + 1 whose distance its result slot holds (0: none)
+  uint32_t spec_k;   // look-ahead budget: extra pass-1/2 alignments a segment may request per round
   uint32_t* og_i;
   int32_t* og_d;
   float* bf_d;       // n+1 per segment, base cbeg + segment index
@@ -157,10 +159,43 @@ struct Machine {
   }
   // a = A (row 0 / horizontal), b = B (row 1 / vertical) as passed to getAlignment(A, B)
   TRPA_HD void emit_pair(uint32_t da, uint32_t db, uint32_t slot) {
-    const uint32_t la = B.descs[da].len, lb = B.descs[db].len;
-    S.cells += (uint64_t)la * lb;
     const uint32_t q = TRPA_ATOMIC_ADD_U32(&B.counters[CN_PAIRS], 1u);
     B.pairs[q] = PairDesc{da, db, slot, 0u};
+  }
+  // cells are counted when an alignment is consumed, i.e. exactly for the alignments the reference
+  // performs; look-ahead results that are never consumed do not count
+  TRPA_HD void count_cells(uint32_t da, uint32_t db) { S.cells += (uint64_t)B.descs[da].len * B.descs[db].len; }
+
+  // Look-ahead (pass 1): while the GPU has idle capacity, also request the alignments of the next
+  // records that would qualify under the CURRENT thresholds.  Decisions are still replayed strictly
+  // in order from exact distances, so results are identical; a look-ahead result is simply found in
+  // the record's slot (tag == anchor + 1) when the loop gets there.
+  TRPA_HD void speculate_p1(uint32_t j0) {
+    uint32_t budget = B.spec_k;
+    const double thr = S.thr_guarantee > S.thr_heur ? S.thr_guarantee : S.thr_heur;
+    for (uint32_t j = j0; budget && j < S.n && rec[j].score >= S.score_thr_i; ++j) {
+      if (j == S.anchor || qd[j] == .0f) continue;
+      if (!(static_cast<double>(qsim[j]) / S.qrlength >= thr)) continue;
+      if (B.tag[S.cbeg + j] == S.anchor + 1u) continue;
+      stage_candidate(j);
+      emit_pair(desc_cand(j), desc_cand(S.anchor), S.cbeg + j);
+      B.tag[S.cbeg + j] = S.anchor + 1u;
+      --budget;
+    }
+  }
+  TRPA_HD void speculate_p2(uint32_t j0) {
+    uint32_t budget = B.spec_k;
+    for (uint32_t j = j0; budget && j < S.n && rec[j].score >= S.score_thr_f; ++j) {
+      if (j == S.anchor) continue;
+      if (!(static_cast<double>(qsim[j]) / S.qrlength >= S.qpid_thresh2)) continue;
+      const uint32_t cnode = rec[j].node;
+      if (tx_is_parent_of(B.tax, S.unode_g, cnode) || cnode == S.unode_g) continue;
+      if (B.tag[S.cbeg + j] == S.anchor + 1u) continue;
+      stage_candidate(j);
+      emit_pair(desc_cand(j), desc_cand(S.anchor), S.cbeg + j);
+      B.tag[S.cbeg + j] = S.anchor + 1u;
+      --budget;
+    }
   }
   TRPA_HD uint32_t desc_cand(uint32_t i) const { return B.n_segs + S.cbeg + i; }
 
@@ -292,6 +327,7 @@ struct Machine {
       bool query_staged = false;
       for (uint32_t i = 0; i < nn; ++i) {
         fl[i] = 0;
+        B.tag[S.cbeg + i] = 0;
         if (rec[i].alnlen == qrlength && rec[i].identities == qrlength) {
           fl[i] = CF_QGROUP;
         } else if (rec[i].score >= thr) {
@@ -302,6 +338,7 @@ struct Machine {
           }
           stage_candidate(i);
           emit_pair(desc_cand(i), s, S.cbeg + i);
+          count_cells(desc_cand(i), s);
           ++S.c0;
         }
       }
@@ -353,14 +390,16 @@ struct Machine {
     }
     if (S.phase == PH_P1_WAIT) {
       float sim;
-      read_alignment(slot_seg, desc_cand(S.i), desc_cand(S.anchor), dist, sim);
+      read_alignment(S.cbeg + S.i, desc_cand(S.i), desc_cand(S.anchor), dist, sim);
+      count_cells(desc_cand(S.i), desc_cand(S.anchor));
       ++S.c1;
       resume_p1 = true;
       goto p1_loop;
     }
     if (S.phase == PH_P2_WAIT_SEG) {
       float sim;
-      read_alignment(slot_seg, desc_cand(S.i), desc_cand(S.anchor), dist, sim);
+      read_alignment(S.cbeg + S.i, desc_cand(S.i), desc_cand(S.anchor), dist, sim);
+      count_cells(desc_cand(S.i), desc_cand(S.anchor));
       ++S.c2;
       qd[S.i] = dist;
       resume_p2 = true;
@@ -405,10 +444,17 @@ struct Machine {
           if (take) {
             if (i == S.anchor) dist = .0f;
             else if (qd[i] == .0f) dist = qd[S.anchor];
-            else {
+            else if (B.tag[S.cbeg + i] == S.anchor + 1u) {  // already computed by look-ahead
+              float sim;
+              read_alignment(S.cbeg + i, desc_cand(i), desc_cand(S.anchor), dist, sim);
+              count_cells(desc_cand(i), desc_cand(S.anchor));
+              ++S.c1;
+            } else {
               stage_candidate(S.anchor);
               stage_candidate(i);
-              emit_pair(desc_cand(i), desc_cand(S.anchor), slot_seg);
+              emit_pair(desc_cand(i), desc_cand(S.anchor), S.cbeg + i);
+              B.tag[S.cbeg + i] = S.anchor + 1u;
+              speculate_p1(i + 1);
               S.phase = PH_P1_WAIT;
               return;
             }
@@ -518,10 +564,18 @@ struct Machine {
             const uint32_t cnode = rec[i].node;
             if (i == anchor) dist = .0f;
             else if (tx_is_parent_of(T, S.unode_g, cnode) || cnode == S.unode_g) take = false;  // "continue"
-            else {
+            else if (B.tag[S.cbeg + i] == anchor + 1u) {  // already computed (look-ahead or pass 1)
+              float sim;
+              read_alignment(S.cbeg + i, desc_cand(i), desc_cand(anchor), dist, sim);
+              count_cells(desc_cand(i), desc_cand(anchor));
+              ++S.c2;
+              qd[i] = dist;
+            } else {
               stage_candidate(anchor);
               stage_candidate(i);
-              emit_pair(desc_cand(i), desc_cand(anchor), slot_seg);
+              emit_pair(desc_cand(i), desc_cand(anchor), S.cbeg + i);
+              B.tag[S.cbeg + i] = anchor + 1u;
+              speculate_p2(i + 1);
               S.phase = PH_P2_WAIT_SEG;
               return;
             }
@@ -536,6 +590,7 @@ struct Machine {
             if (second) {
               float d2, s2;
               read_alignment(slot_seg, desc_cand(anchor), s, d2, s2);
+              count_cells(desc_cand(anchor), s);
               const float sim = s2 < qsim[anchor] ? qsim[anchor] : s2;  // std::max(s2, qsim[anchor])
               qd[anchor] = d2; qsim[anchor] = sim;
               qdist_ex = d2 * S.bandfactor_max;

@@ -34,7 +34,7 @@ class Profile(ctypes.Structure):
 
 
 EXPORTS = ["trpa_abi_version", "trpa_last_error", "trpa_create", "trpa_destroy", "trpa_set_params",
-           "trpa_set_arena_bytes", "trpa_profile_reset", "trpa_profile_get", "trpa_load_taxonomy", "trpa_load_store",
+           "trpa_set_arena_bytes", "trpa_set_lookahead", "trpa_profile_reset", "trpa_profile_get", "trpa_load_taxonomy", "trpa_load_store",
            "trpa_predict_batch", "trpa_batch_upload", "trpa_batch_run", "trpa_batch_download",
            "trpa_edit_distance_batch", "trpa_protein_align_batch", "trpa_fetch_segments", "trpa_lca_batch",
            "trpa_int_alu_peak"]
@@ -96,6 +96,9 @@ class Context:
 
     def set_arena_bytes(self, nbytes):
         self._ck(self.L.trpa_set_arena_bytes(self.h, ctypes.c_uint64(int(nbytes))))
+
+    def set_lookahead(self, k):
+        self._ck(self.L.trpa_set_lookahead(self.h, int(k)))
 
     def load_taxonomy(self, parent, left, right, depth, root=0):
         parent = np.ascontiguousarray(parent, np.uint32); left = np.ascontiguousarray(left, np.uint32)

@@ -24,7 +24,7 @@ extern "C" int hm_predict_batch(
     const uint8_t* r_codes, const uint64_t* r_off, const uint32_t* r_len, uint32_t r_n,
     int protein, float exclude_factor, float toppercent,
     const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands_in, uint32_t n_cands,
-    trpa_result* results, uint32_t* rounds_out) {
+    trpa_result* results, uint32_t* rounds_out, uint32_t spec_k) {
   std::vector<trpa_candidate> cands(cands_in, cands_in + n_cands);
   sort_candidates(segs, n_segs, cands.data());
 
@@ -32,6 +32,7 @@ extern "C" int hm_predict_batch(
   memset(st.data(), 0, sizeof(SegState) * n_segs);
   std::vector<float> qd(n_cands), qsim(n_cands), bf_d(n_cands + n_segs);
   std::vector<uint8_t> cflags(n_cands, 0);
+  std::vector<uint32_t> tag(n_cands, 0);
   std::vector<uint32_t> og_i(n_cands), bf_node(n_cands + n_segs);
   std::vector<int32_t> og_d(n_cands);
   std::vector<int32_t> res_nt(n_cands + n_segs, 0), res_aa(2 * (size_t)(n_cands + n_segs), 0);
@@ -48,6 +49,7 @@ extern "C" int hm_predict_batch(
   B.protein = protein; B.exclude_factor = exclude_factor;
   B.reeval_bandwidth_factor = 1. - toppercent;
   B.st = st.data(); B.qd = qd.data(); B.qsim = qsim.data(); B.cflags = cflags.data();
+  B.tag = tag.data(); B.spec_k = spec_k;
   B.og_i = og_i.data(); B.og_d = og_d.data(); B.bf_d = bf_d.data(); B.bf_node = bf_node.data();
   B.res_nt = res_nt.data(); B.res_aa = res_aa.data();
   B.descs = descs.data(); B.arena_capacity = 0xffffffffu;

@@ -144,7 +144,7 @@ def oracle_predict(fd: FlatData, exclude_factor=0.5, toppercent=0.05, want_pairs
     return (res, logs) if want_pairs else res
 
 
-def host_machine_predict(fd: FlatData, exclude_factor=0.5, toppercent=0.05):
+def host_machine_predict(fd: FlatData, exclude_factor=0.5, toppercent=0.05, spec_k=0):
     H = host_machine()
     n = len(fd.segs)
     res = np.zeros(n, dtype=synth.RESULT_DTYPE)
@@ -158,7 +158,7 @@ def host_machine_predict(fd: FlatData, exclude_factor=0.5, toppercent=0.05):
            ctypes.c_int(int(fd.protein)), ctypes.c_float(exclude_factor), ctypes.c_float(toppercent),
            fd.segs.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(n),
            fd.cands.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(len(fd.cands)),
-           res.ctypes.data_as(ctypes.c_void_p), ctypes.byref(rounds))
+           res.ctypes.data_as(ctypes.c_void_p), ctypes.byref(rounds), ctypes.c_uint32(spec_k))
     assert rc == 0, rc
     return res, rounds.value
 

@@ -22,7 +22,7 @@ def test_header_symbols_exported():
     assert os.path.exists(LIB), "build the extension first: make -C taxator-tk_b200"
     L = ctypes.CDLL(LIB)
     syms = declared_symbols()
-    assert len(syms) >= 19
+    assert len(syms) >= 20
     for s in syms:
         assert hasattr(L, s), s
     assert L.trpa_abi_version() == 1

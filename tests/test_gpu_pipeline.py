@@ -50,6 +50,20 @@ def test_small_arena_chunks(ctx):
     assert ol.results_equal(want, got) == []
 
 
+@pytest.mark.parametrize("k", [0, 2, 64])
+def test_lookahead_is_exact(ctx, k):
+    for case in (CASES[1], CASES[2]):
+        fd = ol.FlatData(synth.generate(synth.SynthConfig(**case)))
+        want = ol.oracle_predict(fd)
+        load(ctx, fd)
+        ctx.set_lookahead(k)
+        try:
+            got = ctx.predict_batch(fd.segs, fd.cands)
+        finally:
+            ctx.set_lookahead(-1)
+        assert ol.results_equal(want, got) == []
+
+
 def test_fetch_and_lca(ctx):
     fd = ol.FlatData(synth.generate(synth.SynthConfig(**CASES[0])))
     load(ctx, fd)

@@ -26,6 +26,11 @@ def test_host_machine_matches_reference_gff3(name):
     assert gu.render_sorted(fd, res) == gu.golden_lines(name)
     assert ol.results_equal(ol.oracle_predict(fd), res) == []
     assert rounds > 1
+    # look-ahead (extra alignments requested per round) never changes a result, only the round count
+    for k in (1, 4, 1000):
+        res_k, rounds_k = ol.host_machine_predict(fd, spec_k=k)
+        assert ol.results_equal(res, res_k) == []
+        assert rounds_k <= rounds
 
 
 def test_oracle_kernels_match_seqan_vectors():

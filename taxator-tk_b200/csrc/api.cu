@@ -36,7 +36,7 @@ template <class F>
 static void parallel_blocks(size_t n, const F& f) {
   unsigned T = std::thread::hardware_concurrency();
   if (T > 16) T = 16;
-  if (T < 2 || n < 4096) { f(0, n); return; }
+  if (T < 2 || n < 65536) { f(0, n); return; }
   std::vector<std::thread> th;
   const size_t per = (n + T - 1) / T;
   for (unsigned t = 0; t < T; ++t) {
@@ -472,22 +472,28 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
   c->n_segs = n_segs; c->n_cands = n_cands;
 
   // arena + chunk plan
-  size_t free_b = 0, total_b = 0;
-  CK(cudaMemGetInfo(&free_b, &total_b));
-  const u64 per_cand = 36 + 4 + 4 + 4 + 1 + 4 + 4 + 4 + 8 + 16 + 32 + 20 + 16;  // rough per-candidate work bytes
-  const u64 fixed = (u64)n_cands * per_cand + (u64)n_segs * (sizeof(SegState) + sizeof(trpa_result) + 96);
-  u64 arena_bytes = c->arena_bytes;
-  if (!arena_bytes) {
-    const u64 avail = free_b > fixed ? free_b - fixed : 0;
-    arena_bytes = avail / 2;
-  }
-  const u64 unit_bytes = protein ? 1 : 12;
-  u64 units_cap = std::min<u64>(arena_bytes / unit_bytes, 0xfffffff0ull);
   u64 total_bound = 0, max_bound = 0; u32 max_len = 0;
   for (u32 s = 0; s < n_segs; ++s) {
     total_bound += bound[s];
     max_bound = std::max(max_bound, bound[s]);
     max_len = std::max(max_len, maxspan[s]);
+  }
+  const u64 unit_bytes = protein ? 1 : 12;
+  const u64 have_units = protein ? (u64)c->arena_aa.cap : std::min<u64>(c->arena_planes.cap, c->arena_n.cap);
+  u64 units_cap;
+  if (!c->arena_bytes && have_units >= total_bound + 16) {
+    units_cap = have_units - 16;   // the arena of an earlier batch is large enough: one chunk, no query
+  } else {
+    u64 arena_bytes = c->arena_bytes;
+    if (!arena_bytes) {
+      size_t free_b = 0, total_b = 0;
+      CK(cudaMemGetInfo(&free_b, &total_b));
+      const u64 per_cand = 36 + 4 + 4 + 4 + 4 + 1 + 4 + 4 + 4 + 8 + 16 + 32 + 20 + 16;  // rough per-candidate work bytes
+      const u64 fixed = (u64)n_cands * per_cand + (u64)n_segs * (sizeof(SegState) + sizeof(trpa_result) + 96);
+      const u64 avail = (free_b > fixed ? free_b - fixed : 0) + have_units * unit_bytes;
+      arena_bytes = avail / 2;
+    }
+    units_cap = std::min<u64>(arena_bytes / unit_bytes, 0xfffffff0ull);
   }
   // extensions can add at most the query range; sequences are clipped to the store anyway
   max_len = std::min<u64>((u64)max_len + Q.max_len, std::max(R.max_len, Q.max_len));

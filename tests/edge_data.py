@@ -1,0 +1,68 @@
+"""Edge-case inputs shared by the CPU (host state machine) and GPU parity tests."""
+import numpy as np
+
+import oracle_lib as ol
+import synth
+
+
+def base(seed=11, protein=False, **kw):
+    cfg = dict(seed=seed, protein=protein, n_genomes=40, genome_len=3000 if not protein else 500, n_queries=80,
+               query_len=(150, 700) if not protein else (60, 250), n_cand=18, levels=(2, 3, 5, 8, 12))
+    cfg.update(kw)
+    return ol.FlatData(synth.generate(synth.SynthConfig(**cfg)))
+
+
+def ranges_past_ends(protein):
+    """Reference coordinates beyond the stored sequence are clipped (sequencestorage.hh:353,
+    faidx.h:325-331); a start past the end yields an empty segment (distance = other length)."""
+    fd = base(seed=21, protein=protein)
+    rng = np.random.default_rng(5)
+    c = fd.cands
+    L = fd.r_len[c["ref_seq"]].astype(np.int64)
+    pick = rng.random(len(c)) < 0.25
+    fwd = c["rstart"] <= c["rstop"]
+    c["rstop"][pick & fwd] = (L[pick & fwd] + rng.integers(1, 500, int((pick & fwd).sum()))).astype(np.uint32)
+    c["rstart"][pick & ~fwd] = (L[pick & ~fwd] + rng.integers(1, 500, int((pick & ~fwd).sum()))).astype(np.uint32)
+    far = rng.random(len(c)) < 0.03
+    c["rstart"][far & fwd] = (L[far & fwd] + 10).astype(np.uint32)
+    c["rstop"][far & fwd] = (L[far & fwd] + 200).astype(np.uint32)
+    return fd
+
+
+def n_rich():
+    fd = base(seed=22, frac_n=0.08)
+    q = fd.q_chars.copy()
+    rng = np.random.default_rng(1)
+    m = rng.random(len(q)) < 0.05
+    q[m] = np.frombuffer(b"NRYKMnacgt-", np.uint8)[rng.integers(0, 11, int(m.sum()))]
+    fd.q_chars = q
+    fd.q_codes = ol.codes_of(q, False)
+    return fd
+
+
+def special_segments():
+    fd = base(seed=23)
+    segs, c = fd.segs, fd.cands
+    segs["cand_count"][0] = 1                      # n == 1 (hh:371-388)
+    segs["cand_count"][1] = 0                      # n == 0 (hh:359-368)
+    s = segs[2]                                    # 100% full-length top hit + a score tie (hh:431-472)
+    b, n = int(s["cand_begin"]), int(s["cand_count"])
+    qs, qe = c["qstart"][b:b + n].min(), c["qstop"][b:b + n].max()
+    L = int(qe - qs + 1)
+    c["qstart"][b], c["qstop"][b] = qs, qe
+    c["alnlen"][b] = L; c["identities"][b] = L; c["score"][b] = 1e6
+    c["score"][b + 1] = 1e6
+    s = segs[3]                                    # identical hit that is NOT the best score (hh:511-517)
+    b, n = int(s["cand_begin"]), int(s["cand_count"])
+    qs, qe = c["qstart"][b:b + n].min(), c["qstop"][b:b + n].max()
+    L = int(qe - qs + 1)
+    worst = b + int(np.argmin(c["score"][b:b + n]))
+    c["qstart"][worst], c["qstop"][worst] = qs, qe
+    c["alnlen"][worst] = L; c["identities"][worst] = L
+    return fd
+
+
+def many_candidates():
+    cfg = synth.SynthConfig(seed=25, n_genomes=300, genome_len=1500, n_queries=6, query_len=(400, 600), n_cand=300,
+                            levels=(3, 6, 12, 30, 80))
+    return ol.FlatData(synth.generate(cfg))

@@ -1,0 +1,37 @@
+"""CPU: the host-compiled product state machine on the edge-case inputs, against the oracle."""
+import pytest
+
+import edge_data
+import oracle_lib as ol
+
+
+def check(fd, **kw):
+    want = ol.oracle_predict(fd, **kw)
+    for k in (0, 5):
+        got, _ = ol.host_machine_predict(fd, spec_k=k, **kw)
+        assert ol.results_equal(want, got) == []
+    return want
+
+
+@pytest.mark.parametrize("protein", [False, True])
+def test_ranges_past_sequence_ends(protein):
+    check(edge_data.ranges_past_ends(protein))
+
+
+def test_n_rich_sequences():
+    check(edge_data.n_rich())
+
+
+def test_special_segments():
+    r = check(edge_data.special_segments())
+    assert r["kind"][0] == 1 and r["kind"][1] == 0 and r["kind"][2] == 2 and r["kind"][3] == 3
+
+
+def test_parameters_x_and_t():
+    fd = edge_data.base(seed=24)
+    for x, t in [(0.0, 0.05), (0.9, 0.05), (0.5, 0.3), (0.5, 0.0)]:
+        check(fd, exclude_factor=x, toppercent=t)
+
+
+def test_many_candidates_one_segment():
+    check(edge_data.many_candidates())

@@ -606,7 +606,8 @@ int trpa_batch_run(trpa_ctx* c) {
           scr = c->scratch_aa.p;
         }
         ev = begin_event(c, EV_PROTEIN);
-        CK(launch_protein(c->d_pairs.p, n_pairs, c->d_descs.p, c->arena_aa.p, (int2*)c->d_res.p, scr, stride, c->stream));
+        CK(launch_protein(c->d_pairs.p, n_pairs, c->d_descs.p, c->arena_aa.p, (int2*)c->d_res.p, scr, stride,
+                          c->max_stage_len, c->stream));
         end_event(c, ev);
         c->prof.launches_protein++;
       } else {
@@ -759,9 +760,9 @@ int trpa_protein_align_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   if (repeat < 1) repeat = 1;
-  if (kernel_ms && repeat > 1) CK(launch_protein(d_pairs.p, n_pairs, d_sd.p, d_codes.p, d_out.p, scr, stride, c->stream));
+  if (kernel_ms && repeat > 1) CK(launch_protein(d_pairs.p, n_pairs, d_sd.p, d_codes.p, d_out.p, scr, stride, max_len, c->stream));
   CK(cudaEventRecord(e0, c->stream));
-  for (int r = 0; r < repeat; ++r) CK(launch_protein(d_pairs.p, n_pairs, d_sd.p, d_codes.p, d_out.p, scr, stride, c->stream));
+  for (int r = 0; r < repeat; ++r) CK(launch_protein(d_pairs.p, n_pairs, d_sd.p, d_codes.p, d_out.p, scr, stride, max_len, c->stream));
   CK(cudaEventRecord(e1, c->stream));
   std::vector<int2> ho(n_pairs);
   CK(cudaMemcpyAsync(ho.data(), d_out.p, sizeof(int2) * n_pairs, cudaMemcpyDeviceToHost, c->stream));

@@ -15,7 +15,7 @@ u32 myers_group_slots(int shape, u32 count);
 // BLOSUM62 linear-gap NW with traced length; out2[pair.out] = {mutual, #diagonal steps}
 // scratch: scratch_stride int2 per pair, needed only when a pair's A is longer than 512 residues
 cudaError_t launch_protein(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,
-                           int2* out2, int2* scratch, u32 scratch_stride, cudaStream_t stream);
+                           int2* out2, int2* scratch, u32 scratch_stride, u32 max_len, cudaStream_t stream);
 
 // ASCII -> packed stores
 cudaError_t launch_pack_nt(const uint8_t* chars, const u64* off, const SeqDesc* seqs, u32 n_seq, u64 total_words,

@@ -10,6 +10,8 @@
 // registers and walks rows (V = sequence B) skewed by l; the right boundary of its block travels to
 // lane l+1 by __shfl_up_sync.  A longer than 32*CMAX columns are processed in column strips with
 // the strip's last column kept in an HBM/L2 scratch line.  BLOSUM62 sits in shared memory.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch.h"
 #include "blosum62_table.h"
@@ -33,7 +35,7 @@ static cudaError_t ensure_table() {
 __global__ void __launch_bounds__(128)
 protein_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __restrict__ seqs,
                const uint8_t* __restrict__ residues, int2* __restrict__ out2, int2* __restrict__ scratch,
-               u32 scratch_stride) {
+               u32 scratch_stride, int skip_below) {
   __shared__ signed char tbl[27 * 32];
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) tbl[i] = c_blosum_p[i >> 5][i & 31];
   __syncthreads();
@@ -47,6 +49,7 @@ protein_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __r
   const uint8_t* b = residues + B.woff;
   const int n = (int)A.len;  // columns (H)
   const int m = (int)B.len;  // rows (V)
+  if (n <= skip_below && m <= skip_below) return;  // handled by protein2_kernel
   int2* my_scratch = scratch + (size_t)warp_gid * scratch_stride;
 
   int res_s = 0, res_nd = 0;
@@ -116,14 +119,34 @@ protein_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __r
   if (lane == 0) out2[pd.out] = make_int2(res_s, res_nd);
 }
 
+cudaError_t launch_protein2(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,
+                            int2* out2, int2* scratch, u32 scratch_stride, cudaStream_t stream);
+int protein2_max_len();
+
+static bool protein_v1_only() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TRPA_PROTEIN_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+// max_len: longest staged sequence of the launch (decides whether the 32-bit fallback kernel runs)
 cudaError_t launch_protein(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,
-                           int2* out2, int2* scratch, u32 scratch_stride, cudaStream_t stream) {
+                           int2* out2, int2* scratch, u32 scratch_stride, u32 max_len, cudaStream_t stream) {
   if (count == 0) return cudaSuccess;
   cudaError_t e = ensure_table();
   if (e != cudaSuccess) return e;
   const u32 blocks = (count + 3) / 4;
-  protein_kernel<<<blocks, 128, 0, stream>>>(pairs, count, seqs, residues, out2, scratch, scratch_stride);
-  return cudaGetLastError();
+  if (protein_v1_only()) {
+    protein_kernel<<<blocks, 128, 0, stream>>>(pairs, count, seqs, residues, out2, scratch, scratch_stride, -1);
+    return cudaGetLastError();
+  }
+  e = launch_protein2(pairs, count, seqs, residues, out2, scratch, scratch_stride, stream);
+  if (e != cudaSuccess) return e;
+  if ((int)max_len > protein2_max_len()) {
+    protein_kernel<<<blocks, 128, 0, stream>>>(pairs, count, seqs, residues, out2, scratch, scratch_stride, protein2_max_len());
+    return cudaGetLastError();
+  }
+  return cudaSuccess;
 }
 
 }  // namespace trpa

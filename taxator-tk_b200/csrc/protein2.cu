@@ -1,0 +1,191 @@
+// Second-generation protein kernel: same result as protein.cu / getAlignmentProtein
+// (core/src/taxonpredictionmodelsequence.hh:173-242: BLOSUM62, linear gap -1, SeqAn tie order
+// diagonal >= vertical >= horizontal, traced alignment length), with the per-cell work cut to
+//   1 LDS.S8 + 1 IMAD (fma pipe) + 2 adds + 1 three-input max + 1 LOP.
+// Each DP cell is ONE packed 32-bit integer
+//     P = score * 2^18 + priority * 2^16 + #gap columns on the traced path
+// so that a single signed max3 picks the best score and, on ties, SeqAn's priority (diagonal 2,
+// vertical 1, horizontal 0); the priority field is cleared before the value is stored.  The traced
+// length follows from the gap count: len = (|A| + |B| + #gaps) / 2.  Substitution scores come from a
+// per-lane "query profile" in shared memory, profile[b][c/4][lane][c%4] = 2*BLOSUM62(a_c, b) + 1 (int8;
+// bank == lane for every access, built with one STS.32 per 4 columns), so the diagonal candidate is one
+// multiply-add: D = profile * 2^17 + diag  (= score + sub, priority 2).
+// Valid while scores fit 14 bits: both sequences <= 700 residues (longer pairs use protein.cu).
+#include "common.cuh"
+#include "launch.h"
+#include "blosum62_table.h"
+
+namespace trpa {
+
+constexpr int kC2Max = 16;
+constexpr int kP2MaxLen = 700;
+constexpr int kP2Warps = 4;
+constexpr int kCQ = kC2Max / 4;
+constexpr size_t kP2ProfBytes = (size_t)kP2Warps * 27 * kCQ * 32 * 4;
+constexpr size_t kP2SmemBytes = kP2ProfBytes + 27 * 32;
+
+__constant__ signed char c_blosum_p2[27][32];
+static bool g_loaded2[16] = {false};
+
+static cudaError_t ensure_table2() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 16 && g_loaded2[dev]) return cudaSuccess;
+  cudaError_t e = cudaMemcpyToSymbol(c_blosum_p2, TRPA_BLOSUM62, sizeof(TRPA_BLOSUM62));
+  if (e == cudaSuccess && dev >= 0 && dev < 16) g_loaded2[dev] = true;
+  return e;
+}
+
+__device__ __forceinline__ int max3i(int a, int b, int c) { return max(max(a, b), c); }
+
+constexpr int SH = 18;
+constexpr int PRIO_MASK = 3 << 16;
+constexpr int CV = -(1 << SH) + (1 << 16) + 1;  // vertical: score-1, priority 1, one more gap column
+constexpr int CH = -(1 << SH) + 1;              // horizontal: score-1, priority 0, one more gap column
+
+// One column strip of <= 32*C columns, C columns per lane, RIGHT aligned: the strip's last column is
+// lane 31's last column and the first (32*C - ns) columns of the low lanes are padding.  A padding
+// column has profile -128 for every residue and row-0 value 0, so neither the diagonal nor the
+// horizontal candidate can win there and the vertical candidate reproduces the left boundary column
+// value (-i, i gaps) in every padding cell -- the first real column sees exactly the boundary it
+// needs.  No per-cell predicates, the wavefront always spans all 32 lanes.  Only the FIRST strip of a
+// pair may be partial (the caller right-aligns the whole sequence); later strips are full.
+template <int C>
+__device__ __forceinline__ int protein2_strip(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int m,
+                                              int s0, int ns, bool first_strip, bool last_strip, signed char* prof,
+                                              const signed char* tbl, int* my_scratch, u32 lane) {
+  constexpr int CQ = (C + 3) / 4;
+  const int pad = 32 * C - ns;                    // leading padding columns of the strip
+  const int v1 = (int)lane * C - pad;             // strip-relative index of this lane's first column (may be < 0)
+  int up[C];
+  int ac[CQ * 4];
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < CQ * 4; ++c) {
+    const int v = v1 + c;
+    ac[c] = (c < C && v >= 0) ? (int)a[s0 + v] : -1;
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const int j = s0 + v1 + c + 1;                // 1-based global column; <= s0 for padding
+    up[c] = (v1 + c >= 0) ? (-j * (1 << SH) + j) : 0;   // padding (first strip only): cell(0, 0)
+  }
+  for (int bb = 0; bb < 27; ++bb) {
+#pragma unroll
+    for (int q = 0; q < CQ; ++q) {
+      u32 w = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = ac[4 * q + k];
+        const int e = r >= 0 ? 2 * tbl[r * 32 + bb] + 1 : -128;
+        w |= (u32)(uint8_t)e << (8 * k);
+      }
+      *reinterpret_cast<u32*>(prof + (bb * CQ + q) * 128) = w;
+    }
+  }
+  __syncwarp();
+  // diagonal input of this lane's first column at row 1 = cell(0, first column - 1)
+  int diag0;
+  {
+    const int v = v1 - 1;                         // strip-relative column left of my first one
+    const int j = s0 + v + 1;
+    diag0 = (v >= 0) ? (-j * (1 << SH) + j) : (-s0 * (1 << SH) + s0);
+  }
+  int last = 0, res = 0;
+  const int steps = m + 31;
+  for (int t = 1; t <= steps; ++t) {
+    const int recv = __shfl_up_sync(0xffffffffu, last, 1);
+    const int i = t - (int)lane;
+    if (i >= 1 && i <= m) {
+      int left;
+      if (lane == 0) left = first_strip ? (-i * (1 << SH) + i) : my_scratch[i];
+      else left = recv;
+      const int left_in = left;
+      int diag = diag0;
+      const signed char* prow = prof + (int)b[i - 1] * (CQ * 128);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int e = prow[(c >> 2) * 128 + (c & 3)];
+        const int D = e * (1 << (SH - 1)) + diag;   // score + sub, priority 2, gaps unchanged
+        const int V = up[c] + CV;
+        const int H = left + CH;
+        const int cell = max3i(D, V, H) & ~PRIO_MASK;
+        diag = up[c];
+        up[c] = cell;
+        left = cell;
+      }
+      diag0 = left_in;
+      last = left;
+      if (lane == 31) {
+        if (!last_strip) my_scratch[i] = left;
+        else if (i == m) res = left;
+      }
+    }
+  }
+  __syncwarp();
+  return __shfl_sync(0xffffffffu, res, 31);
+}
+
+__global__ void __launch_bounds__(128)
+protein2_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __restrict__ seqs,
+                const uint8_t* __restrict__ residues, int2* __restrict__ out2, int2* __restrict__ scratch,
+                u32 scratch_stride) {
+  extern __shared__ __align__(16) signed char prof_all[];
+  signed char* tbl = prof_all + kP2ProfBytes;   // BLOSUM62 [a][b]
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) tbl[i] = c_blosum_p2[i >> 5][i & 31];
+  __syncthreads();
+  const u32 lane = threadIdx.x & 31;
+  const u32 warp_in_cta = threadIdx.x >> 5;
+  const u32 warp_gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp_gid >= count) return;  // whole warp
+  const PairDesc pd = pairs[warp_gid];
+  const SeqDesc A = seqs[pd.a], B = seqs[pd.b];
+  const int n = (int)A.len;  // columns (H)
+  const int m = (int)B.len;  // rows (V)
+  if (n > kP2MaxLen || m > kP2MaxLen) return;  // left to protein_kernel
+  const uint8_t* a = residues + A.woff;
+  const uint8_t* b = residues + B.woff;
+  if (n == 0 || m == 0) {
+    if (lane == 0) out2[pd.out] = make_int2(-(n + m), 0);
+    return;
+  }
+  signed char* prof = prof_all + ((size_t)warp_in_cta * 27 * kCQ * 32 + lane) * 4;  // [b][c/4][lane][c%4]
+  int* my_scratch = reinterpret_cast<int*>(scratch + (size_t)warp_gid * scratch_stride);
+  int res = 0;
+  int ns = ((n - 1) % (32 * kC2Max)) + 1;  // the first strip takes the remainder, later strips are full
+  for (int s0 = 0; s0 < n; s0 += ns, ns = 32 * kC2Max) {
+    const int Cneed = (ns + 31) >> 5;
+    const bool first = s0 == 0, lastS = s0 + ns == n;
+    if (Cneed <= 4) res = protein2_strip<4>(a, b, m, s0, ns, first, lastS, prof, tbl, my_scratch, lane);
+    else if (Cneed <= 8) res = protein2_strip<8>(a, b, m, s0, ns, first, lastS, prof, tbl, my_scratch, lane);
+    else if (Cneed <= 10) res = protein2_strip<10>(a, b, m, s0, ns, first, lastS, prof, tbl, my_scratch, lane);
+    else if (Cneed <= 12) res = protein2_strip<12>(a, b, m, s0, ns, first, lastS, prof, tbl, my_scratch, lane);
+    else res = protein2_strip<16>(a, b, m, s0, ns, first, lastS, prof, tbl, my_scratch, lane);
+  }
+  if (lane == 0) {
+    const int score = res >> SH;            // arithmetic shift: floor, low fields are non-negative
+    const int gaps = res & 0xffff;
+    const int ndiag = (n + m - gaps) / 2;   // |A| + |B| = 2*#diag + #gaps
+    out2[pd.out] = make_int2(score, ndiag);
+  }
+}
+
+cudaError_t launch_protein2(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,
+                            int2* out2, int2* scratch, u32 scratch_stride, cudaStream_t stream) {
+  if (count == 0) return cudaSuccess;
+  cudaError_t e = ensure_table2();
+  if (e != cudaSuccess) return e;
+  static bool attr = false;
+  if (!attr) {
+    e = cudaFuncSetAttribute(protein2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kP2SmemBytes);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const u32 blocks = (count + kP2Warps - 1) / kP2Warps;
+  protein2_kernel<<<blocks, 32 * kP2Warps, kP2SmemBytes, stream>>>(pairs, count, seqs, residues, out2, scratch, scratch_stride);
+  return cudaGetLastError();
+}
+
+int protein2_max_len() { return kP2MaxLen; }
+
+}  // namespace trpa

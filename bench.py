@@ -319,18 +319,19 @@ def main():
     # ---- roofline of the dominant kernel
     if fd.protein:
         k_ms, k_launch = prof["ms_protein"], prof["launches_protein"]
-        # measured cell rate vs a nominal 12 ALU ops per cell
-        peak = alu_peak / 12.0 / 1e9
-        kname = "protein_kernel"
+        # protein2_kernel issues 3 alu-pipe instructions per DP cell (2 VIADDMNMX + 1 LOP3; the
+        # multiply-add of the diagonal runs on the fma pipe, the profile lookup on the LSU)
+        peak = alu_peak / 3.0 / 1e9
+        kname = "protein2_kernel"
     else:
         k_ms, k_launch = prof["ms_edit_distance"], prof["launches_edit_distance"]
         peak = alu_peak * 32.0 / ALU_OPS_PER_WORDSTEP / 1e9
-        kname = "myers_kernel"
+        kname = "myers2_kernel"
     achieved = cells_step * args.steps / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
     roofline = {"bound": "int32_alu", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GCUPS",
                 "frac": achieved / peak if peak else None, "traffic": None,
                 "peak_source": "own probe trpa_int_alu_peak (%.3e lane-ops/s) / %.1f ALU ops per 32-cell word-step"
-                               % (alu_peak, ALU_OPS_PER_WORDSTEP) if not fd.protein else "own probe / 12 ops per cell",
+                               % (alu_peak, ALU_OPS_PER_WORDSTEP) if not fd.protein else "own probe trpa_int_alu_peak / 3 alu ops per cell",
                 "kernel_ms_per_step": k_ms / args.steps, "kernel_share_of_step": (k_ms / args.steps) / ms_step}
     peaks = {}
     try:

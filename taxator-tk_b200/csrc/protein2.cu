@@ -1,16 +1,18 @@
 // Second-generation protein kernel: same result as protein.cu / getAlignmentProtein
 // (core/src/taxonpredictionmodelsequence.hh:173-242: BLOSUM62, linear gap -1, SeqAn tie order
 // diagonal >= vertical >= horizontal, traced alignment length), with the per-cell work cut to
-//   1 LDS.S8 + 1 IMAD (fma pipe) + 2 adds + 1 three-input max + 1 LOP.
+//   1 LDS.U8 + 1 multiply-add + 2 fused add-max (VIADDMNMX) + 1 LOP.
 // Each DP cell is ONE packed 32-bit integer
-//     P = score * 2^18 + priority * 2^16 + #gap columns on the traced path
+//     P = score * 2^13 + priority * 2^11 + #gap columns on the traced path
 // so that a single signed max3 picks the best score and, on ties, SeqAn's priority (diagonal 2,
 // vertical 1, horizontal 0); the priority field is cleared before the value is stored.  The traced
 // length follows from the gap count: len = (|A| + |B| + #gaps) / 2.  Substitution scores come from a
-// per-lane "query profile" in shared memory, profile[b][c/4][lane][c%4] = 2*BLOSUM62(a_c, b) + 1 (int8;
+// per-lane "query profile" in shared memory, profile[b][c/4][lane][c%4] = 2*BLOSUM62(a_c, b) + 9 (uint8;
 // bank == lane for every access, built with one STS.32 per 4 columns), so the diagonal candidate is one
-// multiply-add: D = profile * 2^17 + diag  (= score + sub, priority 2).
-// Valid while scores fit 14 bits: both sequences <= 700 residues (longer pairs use protein.cu).
+// multiply-add: D = profile * 2^12 + diag  (= score + sub, priority 2, plus a constant 2^15 that is
+// carried as a per-row bias i*2^15 on every stored value, so the table stays unsigned and needs no
+// sign extension).  Valid while the gap count fits 11 bits: |A| + |B| <= 2047, i.e. both sequences
+// <= 1000 residues (longer pairs use protein.cu).
 #include "common.cuh"
 #include "launch.h"
 #include "blosum62_table.h"
@@ -18,7 +20,7 @@
 namespace trpa {
 
 constexpr int kC2Max = 16;
-constexpr int kP2MaxLen = 700;
+constexpr int kP2MaxLen = 1000;
 constexpr int kP2Warps = 4;
 constexpr int kCQ = kC2Max / 4;
 constexpr size_t kP2ProfBytes = (size_t)kP2Warps * 27 * kCQ * 32 * 4;
@@ -38,21 +40,23 @@ static cudaError_t ensure_table2() {
 
 __device__ __forceinline__ int max3i(int a, int b, int c) { return max(max(a, b), c); }
 
-constexpr int SH = 18;
-constexpr int PRIO_MASK = 3 << 16;
-constexpr int CV = -(1 << SH) + (1 << 16) + 1;  // vertical: score-1, priority 1, one more gap column
-constexpr int CH = -(1 << SH) + 1;              // horizontal: score-1, priority 0, one more gap column
+constexpr int SH = 13;
+constexpr int PRIO_MASK = 3 << 11;
+constexpr int ROWBIAS = 8 << (SH - 1);                        // what the +8 of the unsigned profile adds per row
+constexpr int CV = -(1 << SH) + (1 << 11) + 1 + ROWBIAS;      // vertical: score-1, priority 1, +1 gap, next row
+constexpr int CH = -(1 << SH) + 1;                            // horizontal: score-1, priority 0, +1 gap
+__device__ __forceinline__ int p2_boundary(int k) { return -k * (1 << SH) + k; }  // score -k after k gap columns
 
 // One column strip of <= 32*C columns, C columns per lane, RIGHT aligned: the strip's last column is
 // lane 31's last column and the first (32*C - ns) columns of the low lanes are padding.  A padding
-// column has profile -128 for every residue and row-0 value 0, so neither the diagonal nor the
+// column has profile 0 (= substitution -4.5) for every residue and row-0 value 0, so neither the diagonal nor the
 // horizontal candidate can win there and the vertical candidate reproduces the left boundary column
 // value (-i, i gaps) in every padding cell -- the first real column sees exactly the boundary it
 // needs.  No per-cell predicates, the wavefront always spans all 32 lanes.  Only the FIRST strip of a
 // pair may be partial (the caller right-aligns the whole sequence); later strips are full.
 template <int C>
 __device__ __forceinline__ int protein2_strip(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int m,
-                                              int s0, int ns, bool first_strip, bool last_strip, signed char* prof,
+                                              int s0, int ns, bool first_strip, bool last_strip, unsigned char* prof,
                                               const signed char* tbl, int* my_scratch, u32 lane) {
   constexpr int CQ = (C + 3) / 4;
   const int pad = 32 * C - ns;                    // leading padding columns of the strip
@@ -68,7 +72,7 @@ __device__ __forceinline__ int protein2_strip(const uint8_t* __restrict__ a, con
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     const int j = s0 + v1 + c + 1;                // 1-based global column; <= s0 for padding
-    up[c] = (v1 + c >= 0) ? (-j * (1 << SH) + j) : 0;   // padding (first strip only): cell(0, 0)
+    up[c] = (v1 + c >= 0) ? p2_boundary(j) : 0;   // padding (first strip only): cell(0, 0)
   }
   for (int bb = 0; bb < 27; ++bb) {
 #pragma unroll
@@ -77,7 +81,7 @@ __device__ __forceinline__ int protein2_strip(const uint8_t* __restrict__ a, con
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int r = ac[4 * q + k];
-        const int e = r >= 0 ? 2 * tbl[r * 32 + bb] + 1 : -128;
+        const int e = r >= 0 ? 2 * tbl[r * 32 + bb] + 9 : 0;
         w |= (u32)(uint8_t)e << (8 * k);
       }
       *reinterpret_cast<u32*>(prof + (bb * CQ + q) * 128) = w;
@@ -89,7 +93,7 @@ __device__ __forceinline__ int protein2_strip(const uint8_t* __restrict__ a, con
   {
     const int v = v1 - 1;                         // strip-relative column left of my first one
     const int j = s0 + v + 1;
-    diag0 = (v >= 0) ? (-j * (1 << SH) + j) : (-s0 * (1 << SH) + s0);
+    diag0 = (v >= 0) ? p2_boundary(j) : p2_boundary(s0);
   }
   int last = 0, res = 0;
   const int steps = m + 31;
@@ -98,15 +102,15 @@ __device__ __forceinline__ int protein2_strip(const uint8_t* __restrict__ a, con
     const int i = t - (int)lane;
     if (i >= 1 && i <= m) {
       int left;
-      if (lane == 0) left = first_strip ? (-i * (1 << SH) + i) : my_scratch[i];
+      if (lane == 0) left = first_strip ? (p2_boundary(i) + i * ROWBIAS) : my_scratch[i];
       else left = recv;
       const int left_in = left;
       int diag = diag0;
-      const signed char* prow = prof + (int)b[i - 1] * (CQ * 128);
+      const unsigned char* prow = prof + (int)b[i - 1] * (CQ * 128);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const int e = prow[(c >> 2) * 128 + (c & 3)];
-        const int D = e * (1 << (SH - 1)) + diag;   // score + sub, priority 2, gaps unchanged
+        const int D = e * (1 << (SH - 1)) + diag;   // score + sub, priority 2, gaps unchanged, row bias + 1
         const int V = up[c] + CV;
         const int H = left + CH;
         const int cell = max3i(D, V, H) & ~PRIO_MASK;
@@ -149,7 +153,7 @@ protein2_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __
     if (lane == 0) out2[pd.out] = make_int2(-(n + m), 0);
     return;
   }
-  signed char* prof = prof_all + ((size_t)warp_in_cta * 27 * kCQ * 32 + lane) * 4;  // [b][c/4][lane][c%4]
+  unsigned char* prof = reinterpret_cast<unsigned char*>(prof_all) + ((size_t)warp_in_cta * 27 * kCQ * 32 + lane) * 4;  // [b][c/4][lane][c%4]
   int* my_scratch = reinterpret_cast<int*>(scratch + (size_t)warp_gid * scratch_stride);
   int res = 0;
   int ns = ((n - 1) % (32 * kC2Max)) + 1;  // the first strip takes the remainder, later strips are full
@@ -163,8 +167,9 @@ protein2_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __
     else res = protein2_strip<16>(a, b, m, s0, ns, first, lastS, prof, tbl, my_scratch, lane);
   }
   if (lane == 0) {
-    const int score = res >> SH;            // arithmetic shift: floor, low fields are non-negative
-    const int gaps = res & 0xffff;
+    const int P = res - m * ROWBIAS;        // remove the per-row bias of the last row
+    const int score = P >> SH;              // arithmetic shift: floor, low fields are non-negative
+    const int gaps = P & 0x7ff;
     const int ndiag = (n + m - gaps) / 2;   // |A| + |B| = 2*#diag + #gaps
     out2[pd.out] = make_int2(score, ndiag);
   }

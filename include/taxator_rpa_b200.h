@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TRPA_ABI_VERSION 1
+#define TRPA_ABI_VERSION 2
 
 #define TRPA_OK 0
 #define TRPA_ERR_CUDA (-1)
@@ -89,13 +89,15 @@ typedef struct trpa_result {
 
 /* Per-kernel device time accumulated since the last reset (CUDA events on the context's stream). */
 typedef struct trpa_profile {
-  double ms_edit_distance;  uint64_t launches_edit_distance;  uint64_t cells_edit_distance;
+  double ms_edit_distance;  uint64_t launches_edit_distance;
+  uint64_t cells_edit_distance;   /* DP cells the edit-distance kernel EXECUTED (band only; <= algorithmic cells) */
   double ms_protein;        uint64_t launches_protein;        uint64_t cells_protein;
   double ms_stage;          uint64_t launches_stage;          uint64_t bytes_stage;
   double ms_decide;         uint64_t launches_decide;
   double ms_other;          uint64_t launches_other;
   uint64_t rounds;
   uint64_t pairs;
+  uint64_t band_retries;          /* pairs re-run with a wider band (first threshold was too small) */
 } trpa_profile;
 
 /* ---- lifecycle --------------------------------------------------------------------------- */
@@ -112,6 +114,14 @@ int trpa_set_arena_bytes(trpa_ctx* ctx, uint64_t bytes);
  * chain of dependent rounds; results are identical for every value).  -1 (default): automatic, only
  * when the GPU has idle capacity; 0: off. */
 int trpa_set_lookahead(trpa_ctx* ctx, int k);
+/* Edit-distance band: 1 (default) = compute only the cells inside an Ukkonen band whose threshold is
+ * an upper bound of the distance (verified, widened and re-run if it was not): same integers, fewer
+ * cells.  0 = the full DP matrix like the reference's bit-vector loop (A/B runs). */
+int trpa_set_band(trpa_ctx* ctx, int on);
+/* Test / tuning hooks (results never depend on them): "band_k0" = forced initial band threshold
+ * (exercises the verify-and-widen loop), "plan_lanes" = lanes the shape planner assumes,
+ * "myers_version" = 2 selects the previous full-matrix kernel for A/B runs. */
+int trpa_set_tuning(trpa_ctx* ctx, const char* key, int64_t value);
 int trpa_profile_reset(trpa_ctx* ctx);
 int trpa_profile_get(trpa_ctx* ctx, trpa_profile* out);
 

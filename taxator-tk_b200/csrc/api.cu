@@ -5,6 +5,7 @@
 // Compile with --fmad=false (decision arithmetic must match the reference's IEEE float/double ops).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -122,7 +123,13 @@ struct trpa_ctx {
   DevBuf<uint8_t> arena_aa;
   u64 arena_units = 0;
   DevBuf<u32> scratch;
+  DevBuf<uint4> scratch3;     // banded kernel: wrap-around strip boundaries, one line per group slot
+  DevBuf<unsigned long long> d_plan;  // [1..3] {word-blocks, retries, pairs} of myers3
   DevBuf<int2> scratch_aa;
+  int band = 1;               // 1: Ukkonen band (exact), 0: full DP matrix
+  int myers_version = 3;      // 3: banded rotating-strip kernel, 2: myers2 (A/B runs, TRPA_MYERS=2)
+  u32 band_k0 = 0;            // test hook: forced initial threshold (0 = planned), exercises the retry loop
+  u32 plan_lanes = 0;         // test hook: lanes the shape planner assumes (0 = num_sms * 16 warps * 32)
   u32* h_counters = nullptr;  // pinned: kNumCounters round counters + kNumShapes shape histogram
   int num_sms = 148;
   // profiling
@@ -173,7 +180,7 @@ __global__ void scan_kernel(u32* hist, uint2* buckets) {
 __global__ void scatter_kernel(const PairDesc* pairs, u32 n, u32* hist, PairDesc* sorted) {
   for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const PairDesc p = pairs[k];
-    const u32 pos = atomicAdd(&hist[kNumShapes + p.pad], 1u);
+    const u32 pos = atomicAdd(&hist[kNumShapes + (p.pad & 0xffu)], 1u);   // pad: shape | k0 << 8
     sorted[pos] = p;
   }
 }
@@ -264,6 +271,70 @@ static int launch_myers_shapes(trpa_ctx* c, const u32* h_hist, const PairDesc* s
   return 0;
 }
 
+
+// ---- banded path: plan (threshold + shape per pair), counting sort by shape, one launch per shape
+static int bucket_pairs3(trpa_ctx* c, PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, const uint2* planes,
+                         const u32* nplane, PairDesc* sorted, u32* h_hist) {
+  if (!c->d_plan.p) {
+    if (c->d_plan.ensure(4)) return TRPA_ERR_NOMEM;
+    CK(cudaMemsetAsync(c->d_plan.p, 0, 4 * sizeof(unsigned long long), c->stream));
+  }
+  CK(cudaMemsetAsync(c->d_hist.p, 0, sizeof(u32) * 3 * kNumShapes, c->stream));
+  const u32 blocks = std::min<u32>((n_pairs + 255) / 256, 148 * 8);
+  CK(launch_plan(pairs, n_pairs, descs, planes, nplane, c->d_hist.p, c->plan_lanes ? c->plan_lanes : (u32)c->num_sms * 16u * 32u,
+                 c->band ? (c->band_k0 ? (int)c->band_k0 : 1) : 0, c->stream));
+  scan_kernel<<<1, 32, 0, c->stream>>>(c->d_hist.p, c->d_buckets.p);
+  scatter_kernel<<<blocks, 256, 0, c->stream>>>(pairs, n_pairs, c->d_hist.p, sorted);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h_hist, c->d_hist.p, sizeof(u32) * kNumShapes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static int launch_myers_shapes3(trpa_ctx* c, const u32* h_hist, const PairDesc* sorted, const SeqDesc* descs,
+                                const uint2* planes, const u32* nplane, int* out, u32 max_len) {
+  const u32 stride = (max_len + 31) / 32 + 1;
+  CK(cudaMemsetAsync(c->d_hist.p + 2 * kNumShapes, 0, sizeof(u32) * kNumShapes, c->stream));
+  u32 max_slots = 0;
+  for (int shape = 0; shape < kNumShapes; ++shape) {
+    if (!h_hist[shape]) continue;
+    u32 slots = 0;
+    CK(launch_myers3(shape, nullptr, h_hist[shape], nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, &slots, c->stream));
+    max_slots = std::max(max_slots, slots);
+  }
+  // kernels of one stream run back to back, so one scratch area serves all shapes
+  if (c->scratch3.ensure((size_t)max_slots * stride + 1)) return TRPA_ERR_NOMEM;
+  static const bool debug = getenv("TRPA_DEBUG") != nullptr;
+  if (debug) {
+    fprintf(stderr, "[trpa] myers3 round:");
+    for (int shape = 0; shape < kNumShapes; ++shape)
+      if (h_hist[shape]) fprintf(stderr, " W%dxL%d%s:%u", shape_W(shape_widx(shape)), 1 << shape_lidx(shape), shape_hasn(shape) ? "N" : "", h_hist[shape]);
+    fprintf(stderr, "\n");
+  }
+  u32 start = 0;
+  for (int shape = 0; shape < kNumShapes; ++shape) {
+    const u32 cnt = h_hist[shape];
+    if (!cnt) continue;
+    CK(launch_myers3(shape, sorted + start, cnt, descs, planes, nplane, out, c->scratch3.p, stride,
+                     c->d_hist.p + 2 * kNumShapes + shape, c->d_plan.p + 1, c->band ? 0 : 1, nullptr, c->stream));
+    c->prof.launches_edit_distance++;
+    start += cnt;
+  }
+  return 0;
+}
+
+// {word-blocks, retries, pairs} of the banded kernel since the last call -> profile
+static int harvest_band_stats(trpa_ctx* c) {
+  if (!c->d_plan.p) return 0;
+  unsigned long long h[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(h, c->d_plan.p + 1, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemsetAsync(c->d_plan.p + 1, 0, sizeof(h), c->stream));
+  c->prof.cells_edit_distance += h[0] * 1024ull;
+  c->prof.band_retries += h[1];
+  return 0;
+}
+
 }  // namespace trpa
 
 // =========================================================================================== ABI
@@ -292,6 +363,8 @@ trpa_ctx* trpa_create(int device, void* cuda_stream) {
   }
   if (cudaMallocHost(&c->h_counters, sizeof(u32) * (kNumCounters + 2 * kNumShapes)) != cudaSuccess) { set_error("cudaMallocHost failed"); delete c; return nullptr; }
   if (cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->num_sms <= 0) c->num_sms = 148;
+  if (const char* e = getenv("TRPA_BAND")) c->band = e[0] != '0';
+  if (const char* e = getenv("TRPA_MYERS")) c->myers_version = e[0] == '2' ? 2 : 3;
   return c;
 }
 
@@ -306,7 +379,7 @@ void trpa_destroy(trpa_ctx* c) {
   c->d_bf_node.release(); c->d_og_d.release(); c->d_res.release(); c->d_descs.release(); c->d_pairs.release();
   c->d_pairs_sorted.release(); c->d_stage.release(); c->d_counters.release(); c->d_hist.release();
   c->d_buckets.release(); c->arena_planes.release(); c->arena_n.release(); c->arena_aa.release();
-  c->scratch.release(); c->scratch_aa.release();
+  c->scratch.release(); c->scratch_aa.release(); c->scratch3.release(); c->d_plan.release();
   for (auto& e : c->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -326,6 +399,20 @@ int trpa_set_arena_bytes(trpa_ctx* c, uint64_t bytes) {
 int trpa_set_lookahead(trpa_ctx* c, int k) {
   if (!c) { set_error("null ctx"); return TRPA_ERR_ARG; }
   c->lookahead = k < 0 ? -1 : k;
+  return 0;
+}
+int trpa_set_band(trpa_ctx* c, int on) {
+  if (!c) { set_error("null ctx"); return TRPA_ERR_ARG; }
+  c->band = on ? 1 : 0;
+  return 0;
+}
+int trpa_set_tuning(trpa_ctx* c, const char* key, int64_t value) {
+  if (!c || !key) { set_error("bad arguments"); return TRPA_ERR_ARG; }
+  const std::string k(key);
+  if (k == "band_k0") c->band_k0 = value < 0 ? 0u : (u32)std::min<int64_t>(value, 0xfffffe);
+  else if (k == "plan_lanes") c->plan_lanes = value < 0 ? 0u : (u32)std::min<int64_t>(value, 1 << 30);
+  else if (k == "myers_version") c->myers_version = value == 2 ? 2 : 3;
+  else { set_error("unknown tuning key: " + k); return TRPA_ERR_ARG; }
   return 0;
 }
 int trpa_profile_reset(trpa_ctx* c) { if (!c) return TRPA_ERR_ARG; memset(&c->prof, 0, sizeof(c->prof)); return 0; }
@@ -584,6 +671,7 @@ int trpa_batch_run(trpa_ctx* c) {
         // (nt: 3 planes x 4 B per 32-base word each way; aa: 5 bit read + 1 byte written per residue)
         const u64 units = c->h_counters[CN_ARENA];
         c->prof.bytes_stage += protein ? (units * 13) / 8 : units * 24;
+        if (!protein && c->myers_version == 3) { const int rc = harvest_band_stats(c); if (rc) return rc; }
         break;
       }
       c->prof.rounds++;
@@ -613,13 +701,17 @@ int trpa_batch_run(trpa_ctx* c) {
       } else {
         ev = begin_event(c, EV_OTHER);
         u32* h_hist = c->h_counters + kNumCounters;
-        int rc = bucket_pairs(c, c->d_pairs.p, n_pairs, c->d_descs.p, c->d_pairs_sorted.p, h_hist);
+        const bool v3 = c->myers_version == 3;
+        int rc = v3 ? bucket_pairs3(c, c->d_pairs.p, n_pairs, c->d_descs.p, c->arena_planes.p, c->arena_n.p, c->d_pairs_sorted.p, h_hist)
+                    : bucket_pairs(c, c->d_pairs.p, n_pairs, c->d_descs.p, c->d_pairs_sorted.p, h_hist);
         if (rc) return rc;
         end_event(c, ev);
-        c->prof.launches_other += 3;
+        c->prof.launches_other += v3 ? 4 : 3;
         ev = begin_event(c, EV_MYERS);
-        rc = launch_myers_shapes(c, h_hist, c->d_pairs_sorted.p, c->d_descs.p, c->arena_planes.p, c->arena_n.p,
-                                 c->d_res.p, c->max_stage_len);
+        rc = v3 ? launch_myers_shapes3(c, h_hist, c->d_pairs_sorted.p, c->d_descs.p, c->arena_planes.p, c->arena_n.p,
+                                       c->d_res.p, c->max_stage_len)
+                : launch_myers_shapes(c, h_hist, c->d_pairs_sorted.p, c->d_descs.p, c->arena_planes.p, c->arena_n.p,
+                                      c->d_res.p, c->max_stage_len);
         if (rc) return rc;
         end_event(c, ev);
       }
@@ -699,7 +791,9 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   for (u32 k = 0; k < n_pairs; ++k) hp[k] = PairDesc{pair_a[k], pair_b[k], k, 0};
   CK(cudaMemcpyAsync(d_pairs.p, hp.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, c->stream));
   std::vector<u32> h_hist(kNumShapes, 0);
-  rc = bucket_pairs(c, d_pairs.p, n_pairs, d_sd.p, d_sorted.p, c->h_counters + kNumCounters);
+  const bool v3 = c->myers_version == 3;
+  rc = v3 ? bucket_pairs3(c, d_pairs.p, n_pairs, d_sd.p, planes.p, nplane.p, d_sorted.p, c->h_counters + kNumCounters)
+          : bucket_pairs(c, d_pairs.p, n_pairs, d_sd.p, d_sorted.p, c->h_counters + kNumCounters);
   if (rc) return rc;
   memcpy(h_hist.data(), c->h_counters + kNumCounters, sizeof(u32) * kNumShapes);
   cudaEvent_t e0, e1;
@@ -707,12 +801,14 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   if (repeat < 1) repeat = 1;
   // one untimed pass when timing is requested
   if (kernel_ms && repeat > 1) {
-    rc = launch_myers_shapes(c, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
+    rc = v3 ? launch_myers_shapes3(c, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len)
+            : launch_myers_shapes(c, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
     if (rc) return rc;
   }
   CK(cudaEventRecord(e0, c->stream));
   for (int r = 0; r < repeat; ++r) {
-    rc = launch_myers_shapes(c, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
+    rc = v3 ? launch_myers_shapes3(c, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len)
+            : launch_myers_shapes(c, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
     if (rc) return rc;
   }
   CK(cudaEventRecord(e1, c->stream));
@@ -722,6 +818,7 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   CK(cudaEventElapsedTime(&ms, e0, e1));
   if (kernel_ms) *kernel_ms = ms / repeat;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (v3) { rc = harvest_band_stats(c); if (rc) return rc; }
   d_chars.release(); d_off.release(); d_sd.release(); planes.release(); nplane.release(); d_pairs.release();
   d_sorted.release(); d_out.release(); d_cnt.release(); d_flags.release();
   return 0;

@@ -12,6 +12,17 @@ cudaError_t launch_myers(int shape, const PairDesc* pairs, u32 count, const SeqD
                          u32* cursor, cudaStream_t stream);
 u32 myers_group_slots(int shape, u32 count);
 
+// banded edit distance (myers3.cuh).  launch_plan: initial threshold k0 + shape of every pair of the
+// round (PairDesc.pad: hint on entry; bits 0..7 shape, 8..31 k0 on exit) and the per-shape histogram.
+// band: 0 = full matrix, 1 = band, > 1 = band with that forced initial threshold (test hook).
+cudaError_t launch_plan(PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, const uint2* planes, const u32* nplane,
+                        u32* hist, u32 lanes_total, int band, cudaStream_t stream);
+// pairs[0..count) all of `shape`; scratch: scratch_stride uint4 per group slot (slots_out != nullptr:
+// only report how many slots the launch would use); stats: {word-blocks, retries, pairs} accumulators
+cudaError_t launch_myers3(int shape, const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint2* planes,
+                          const u32* nplane, int* out, uint4* scratch, u32 scratch_stride, u32* cursor,
+                          unsigned long long* stats, int force_full, u32* slots_out, cudaStream_t stream);
+
 // BLOSUM62 linear-gap NW with traced length; out2[pair.out] = {mutual, #diagonal steps}
 // scratch: scratch_stride int2 per pair, needed only when a pair's A is longer than 512 residues
 cudaError_t launch_protein(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,

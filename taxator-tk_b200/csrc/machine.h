@@ -158,9 +158,27 @@ struct Machine {
     B.stage[q] = StageReq{desc, store, seq, (uint32_t)b, rev};
   }
   // a = A (row 0 / horizontal), b = B (row 1 / vertical) as passed to getAlignment(A, B)
-  TRPA_HD void emit_pair(uint32_t da, uint32_t db, uint32_t slot) {
+  // hint: estimate of the distance (0 = none).  It only seeds the band of the edit-distance kernel,
+  // which verifies it and widens the band when it was too small: results never depend on it.
+  TRPA_HD void emit_pair(uint32_t da, uint32_t db, uint32_t slot, uint32_t hint = 0u) {
     const uint32_t q = TRPA_ATOMIC_ADD_U32(&B.counters[CN_PAIRS], 1u);
-    B.pairs[q] = PairDesc{da, db, slot, 0u};
+    B.pairs[q] = PairDesc{da, db, slot, hint};
+  }
+  // the aligner's own alignment of record i (alnlen columns, `identities` matches) is an edit script
+  // of its query range; scaled to the whole query range of the segment
+  TRPA_HD uint32_t hint_query(uint32_t i) const {
+    const trpa_candidate& r = rec[i];
+    if (r.alnlen == 0 || r.identities > r.alnlen) return 0u;
+    const uint64_t e = (uint64_t)(r.alnlen - r.identities) * S.qrlength / r.alnlen;
+    return (uint32_t)(e < 0x7fffffffu ? e + 1u : 0x7fffffffu);
+  }
+  // segment i <-> segment j: triangle inequality over the query, exact query distances where known
+  TRPA_HD uint32_t hint_pair(uint32_t i, uint32_t j) const {
+    if (B.protein) return 0u;
+    const float di = qd[i] != FLT_MAX && (fl[i] & CF_P0_ALIGNED) ? qd[i] : (float)hint_query(i);
+    const float dj = qd[j] != FLT_MAX && (fl[j] & CF_P0_ALIGNED) ? qd[j] : (float)hint_query(j);
+    const float e = di + dj;
+    return e < 2.0e9f ? (uint32_t)e + 1u : 0x7fffffffu;
   }
   // cells are counted when an alignment is consumed, i.e. exactly for the alignments the reference
   // performs; look-ahead results that are never consumed do not count
@@ -178,7 +196,7 @@ struct Machine {
       if (!(static_cast<double>(qsim[j]) / S.qrlength >= thr)) continue;
       if (B.tag[S.cbeg + j] == S.anchor + 1u) continue;
       stage_candidate(j);
-      emit_pair(desc_cand(j), desc_cand(S.anchor), S.cbeg + j);
+      emit_pair(desc_cand(j), desc_cand(S.anchor), S.cbeg + j, hint_pair(j, S.anchor));
       B.tag[S.cbeg + j] = S.anchor + 1u;
       --budget;
     }
@@ -192,7 +210,7 @@ struct Machine {
       if (tx_is_parent_of(B.tax, S.unode_g, cnode) || cnode == S.unode_g) continue;
       if (B.tag[S.cbeg + j] == S.anchor + 1u) continue;
       stage_candidate(j);
-      emit_pair(desc_cand(j), desc_cand(S.anchor), S.cbeg + j);
+      emit_pair(desc_cand(j), desc_cand(S.anchor), S.cbeg + j, hint_pair(j, S.anchor));
       B.tag[S.cbeg + j] = S.anchor + 1u;
       --budget;
     }
@@ -337,7 +355,7 @@ struct Machine {
             query_staged = true;
           }
           stage_candidate(i);
-          emit_pair(desc_cand(i), s, S.cbeg + i);
+          emit_pair(desc_cand(i), s, S.cbeg + i, B.protein ? 0u : hint_query(i));
           count_cells(desc_cand(i), s);
           ++S.c0;
         }
@@ -452,7 +470,7 @@ struct Machine {
             } else {
               stage_candidate(S.anchor);
               stage_candidate(i);
-              emit_pair(desc_cand(i), desc_cand(S.anchor), S.cbeg + i);
+              emit_pair(desc_cand(i), desc_cand(S.anchor), S.cbeg + i, hint_pair(i, S.anchor));
               B.tag[S.cbeg + i] = S.anchor + 1u;
               speculate_p1(i + 1);
               S.phase = PH_P1_WAIT;
@@ -573,7 +591,7 @@ struct Machine {
             } else {
               stage_candidate(anchor);
               stage_candidate(i);
-              emit_pair(desc_cand(i), desc_cand(anchor), S.cbeg + i);
+              emit_pair(desc_cand(i), desc_cand(anchor), S.cbeg + i, hint_pair(i, anchor));
               B.tag[S.cbeg + i] = anchor + 1u;
               speculate_p2(i + 1);
               S.phase = PH_P2_WAIT_SEG;
@@ -597,7 +615,7 @@ struct Machine {
               ++S.c2;
             } else if (qd[anchor] == FLT_MAX) {
               stage_candidate(anchor);
-              emit_pair(desc_cand(anchor), s, slot_seg);
+              emit_pair(desc_cand(anchor), s, slot_seg, B.protein ? 0u : hint_query(anchor));
               S.pend_dist = dist;
               S.phase = PH_P2_WAIT_QRY;
               return;

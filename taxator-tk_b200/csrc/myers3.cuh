@@ -1,0 +1,291 @@
+// Third-generation edit-distance kernel: the same integer as myers.cuh / myers2.cuh / hh:150, but
+// only the cells inside an Ukkonen band are computed (exact: see below), and the pattern strips of
+// a pair ROTATE over the lanes of its group so that a band of any width keeps every lane busy.
+//
+//  * pair (m <= n, delta = n - m), threshold k >= delta: every alignment of cost <= k stays inside
+//    the diagonals [-a, delta + a], a = (k - delta) / 2.  Strip s (32*W pattern rows) therefore
+//    only needs the text blocks b0(s)..b1(s) (32 columns each) that intersect that band.
+//  * outside the computed region the DP is replaced by upper bounds: a strip starts its first block
+//    with VP = all ones (vertical deltas +1) and, for blocks the strip above never computed, takes
+//    horizontal deltas +1 as its top boundary.  Hence the computed value v >= d always, and v == d
+//    whenever v <= k (then an optimal path lies inside the band and is computed exactly).  v > k
+//    proves d > k: the group widens the band (k <- min(v, 3k); v itself is an upper bound of d) and
+//    runs the pair again.  k = n is always sufficient (d <= n), so the loop ends.
+//  * schedule: a group of L lanes owns the pair; strip s runs on lane s % L in round r = s / L; at
+//    group step t it works on block t - T0(s), T0 = offset_r + (s % L), so a strip is always exactly
+//    one block behind the strip above it: lanes 1..L-1 take their top boundary (HP/HN shift-out
+//    bits, adder carries, running bottom-row value) from the lane above by shuffle; lane 0 takes it
+//    from a per-group scratch line in L2 that lane L-1 wrote at least one step earlier (prefetched
+//    one step ahead).  offset_{r+1} - offset_r = L + gap_r with gap_r just large enough that no lane
+//    has to start a strip before it finished the previous one.
+//  * the score is assembled from deltas: corner(s) (value above the strip at its first column,
+//    handed down the same way) + the top-boundary deltas of the last strip + popc(VP) - popc(VN) of
+//    the last column.
+// scripts/band_model.py is an executable model of exactly this schedule (checked against a plain DP).
+#pragma once
+#include "myers2.cuh"
+#include "shapes.h"
+
+namespace trpa {
+
+__device__ __forceinline__ uint4 ldcg_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stcg_u4(uint4* p, uint4 v) {
+  asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// PairDesc.pad as written by plan_kernel: bits 0..7 shape id, bits 8..31 initial threshold k0
+// (kPadKFull = no band).
+constexpr u32 kPadKFull = 0xffffffu;
+
+// stats[0] += executed 32x32-cell word-blocks, stats[1] += band retries, stats[2] += pairs
+template <int W, bool HASN>
+__global__ void __launch_bounds__(128)
+myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __restrict__ seqs,
+              const uint2* __restrict__ planes, const u32* __restrict__ nplane, int* __restrict__ out, int L,
+              uint4* __restrict__ scratch, u32 scratch_stride, const uint2* __restrict__ bucket,
+              u32* __restrict__ cursor, unsigned long long* __restrict__ stats, int force_full) {
+  typedef Myers2Cfg<W, HASN> Cfg;
+  constexpr int WQ = Cfg::WQ;
+  constexpr int NSYM = Cfg::NSYM;
+  constexpr u32 R = 32u * W;
+  extern __shared__ uint4 eqtab[];
+  if (bucket) {
+    const uint2 bk = *bucket;
+    pairs += bk.x;
+    count = bk.y;
+  }
+  const u32 lane = threadIdx.x & 31;
+  const u32 warp_in_cta = threadIdx.x >> 5;
+  const u32 G = 32 / L;
+  const u32 g = lane / L;
+  const u32 sl = lane - g * L;
+  const bool in_group = g < G;   // L need not divide 32: leftover lanes idle
+  const u32 gmask = (L == 32 ? 0xffffffffu : ((1u << L) - 1u) << (g * L));
+  const u32 warp_gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 slot = warp_gid * G + g;
+  uint4* my = eqtab + (size_t)warp_in_cta * NSYM * WQ * 32 + lane;   // entry(sym, wq) = my[(sym*WQ + wq)*32]
+  uint4* my_scratch = scratch + (size_t)slot * scratch_stride;
+
+  bool active = false, exhausted = !in_group, need_setup = false;
+  // pair (uniform inside a group)
+  u32 m = 0, n = 0, pw = 0, tw = 0, oidx = 0, mwords = 0, S = 0, a = 0, ua = 0, k = 0, t = 0;
+  // lane
+  u32 s = 0, r = 0, T0 = 0, sb0 = 0, sb1 = 0, pb1 = 0;
+  int corner = 0, botacc = 0, tsum = 0, vfinal = 0;
+  u32 VP[W], VN[W];
+  u32 hpOut = 0, hnOut = 0, cOut = 0;
+  uint4 pre = make_uint4(0u, 0u, 0u, 0u);
+  bool have_pre = false;
+  u32 nblocks = 0, nretry = 0, npairs = 0;
+
+  auto gb0 = [&](u32 st) -> u32 { const u32 x = st * R; return x > a ? (x - a) >> 5 : 0u; };
+  auto gb1 = [&](u32 st) -> u32 { const u32 hi = (st + 1u) * R - 1u + ua; return (hi < n - 1u ? hi : n - 1u) >> 5; };
+  auto set_band = [&](u32 kk) {
+    const BandGeom bg = band_from_k(m, n, kk, force_full != 0);
+    a = bg.a; ua = bg.ua; k = bg.k;
+  };
+  auto start_attempt = [&]() {
+    t = 0; s = sl; r = 0; T0 = sl;
+    need_setup = s < S;
+    hpOut = 0; hnOut = 0; cOut = 0; botacc = 0;
+  };
+  auto setup_strip = [&]() {
+    sb0 = gb0(s); sb1 = gb1(s); pb1 = s ? gb1(s - 1u) : 0u;
+    const u32 kbase = s * W;
+#pragma unroll
+    for (int q = 0; q < WQ; ++q) {
+      u32 e[NSYM][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int w = 4 * q + j;
+        uint2 p = make_uint2(0u, 0u);
+        u32 pn = 0;
+        if (w < W && kbase + w < mwords) {
+          p = planes[pw + kbase + w];
+          if (HASN) pn = nplane[pw + kbase + w];
+        }
+        e[0][j] = ~(p.x | p.y | pn);   // A
+        e[1][j] = p.x & ~p.y;          // C
+        e[2][j] = ~p.x & p.y;          // G
+        e[3][j] = p.x & p.y;           // T
+        if (HASN) e[NSYM - 1][j] = pn; // N matches N
+      }
+#pragma unroll
+      for (int sym = 0; sym < NSYM; ++sym) my[(sym * WQ + q) * 32] = make_uint4(e[sym][0], e[sym][1], e[sym][2], e[sym][3]);
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) { VP[w] = 0xffffffffu; VN[w] = 0u; }
+    tsum = 0;
+    have_pre = false;
+  };
+  // extra steps between round r and r+1 so that no lane starts a strip before finishing the previous one
+  auto round_gap = [&](u32 rr) -> u32 {
+    u32 gp = 1;
+    for (u32 l = 0; l < (u32)L; ++l) {
+      const u32 st = rr * L + l;
+      if (st + L >= S) break;
+      const int term = (int)gb1(st) - (int)gb0(st + L) + 1 - L;
+      if (term > (int)gp) gp = (u32)term;
+    }
+    return gp;
+  };
+
+  for (;;) {
+    if (!active && !exhausted) {  // uniform inside a group
+      u32 idx = 0;
+      if (sl == 0) idx = atomicAdd(cursor, 1u);
+      idx = __shfl_sync(gmask, idx, g * L);
+      if (idx >= count) exhausted = true;
+      else {
+        const PairDesc pd = pairs[idx];
+        const SeqDesc A = seqs[pd.a], B = seqs[pd.b];
+        if (A.len < B.len) { m = A.len; pw = A.woff; n = B.len; tw = B.woff; }
+        else               { m = B.len; pw = B.woff; n = A.len; tw = A.woff; }
+        oidx = pd.out;
+        mwords = (m + 31) >> 5;
+        if (sl == 0) ++npairs;
+        if (m == 0) {
+          if (sl == 0) out[oidx] = (int)n;   // empty pattern: n insertions (m <= n)
+        } else {
+          S = (mwords + W - 1) / W;
+          const u32 k0 = pd.pad >> 8;
+          set_band(k0 >= kPadKFull ? 0xffffffffu : k0);
+          start_attempt();
+          active = true;
+        }
+      }
+    }
+    if (__all_sync(0xffffffffu, !active && exhausted)) break;
+
+    // boundary handed down by the lane above (its outputs of the previous step)
+    const u32 src = sl == 0 ? lane : lane - 1;
+    const u32 hpIn = __shfl_sync(0xffffffffu, hpOut, src);
+    const u32 hnIn = __shfl_sync(0xffffffffu, hnOut, src);
+    const u32 cIn = __shfl_sync(0xffffffffu, cOut, src);
+    const int botIn = __shfl_sync(0xffffffffu, botacc, src);
+
+    bool do_block = false, islast = false, fin_lane = false;
+    u32 hpc = 0, hnc = 0, cc = 0, run = 32, b = 0;
+    if (active && s < S) {
+      if (need_setup) { setup_strip(); need_setup = false; }
+      const int bi = (int)t - (int)T0;
+      if (bi >= (int)sb0) {
+        do_block = true;
+        b = (u32)bi;
+        int boti = 0;
+        if (s > 0 && b <= pb1) {  // the strip above computed this block
+          if (sl == 0) {
+            const uint4 q = have_pre ? pre : ldcg_u4(my_scratch + b);
+            hpc = q.x; hnc = q.y; cc = q.z; boti = (int)q.w;
+          } else { hpc = hpIn; hnc = hnIn; cc = cIn; boti = botIn; }
+        } else { hpc = 0xffffffffu; hnc = 0u; cc = 0u; }   // row 0, or upper bound (+1 deltas)
+        if (b == sb0) {
+          corner = s ? boti - (__popc(hpc) - __popc(hnc)) : 0;
+          botacc = corner + (int)R;
+        }
+        have_pre = false;
+        if (sl == 0 && s > 0 && b + 1u <= (sb1 < pb1 ? sb1 : pb1)) { pre = ldcg_u4(my_scratch + b + 1u); have_pre = true; }
+        islast = s + 1u == S;
+        if (islast) {
+          const u32 ncols = min(32u, n - 32u * b);
+          run = ncols;
+          const u32 vm = 0xffffffffu << (32u - ncols);
+          tsum += __popc(hpc & vm) - __popc(hnc & vm);
+        }
+      }
+    }
+    const bool any_partial = __any_sync(0xffffffffu, do_block && run < 32u);
+    if (do_block) {
+      const uint2 tx = planes[tw + b];
+      u32 t0 = __brev(tx.x), t1 = __brev(tx.y), tN = 0;
+      if (HASN) tN = __brev(nplane[tw + b]);
+      hpOut = 0; hnOut = 0; cOut = 0;
+      auto column = [&]() {
+        u32 sym = (t0 >> 31) + 2u * (t1 >> 31);
+        if (HASN) sym = (tN >> 31) ? (u32)(NSYM - 1) : sym;
+        const uint4* row = my + sym * (WQ * 32);
+        u32 Eq[W];
+#pragma unroll
+        for (int q = 0; q < WQ; ++q) {
+          const uint4 e = row[q * 32];
+          if (4 * q + 0 < W) Eq[4 * q + 0] = e.x;
+          if (4 * q + 1 < W) Eq[4 * q + 1] = e.y;
+          if (4 * q + 2 < W) Eq[4 * q + 2] = e.z;
+          if (4 * q + 3 < W) Eq[4 * q + 3] = e.w;
+        }
+        myers2_column<W>(VP, VN, Eq, hpc, hnc, cc, hpOut, hnOut, cOut);
+        t0 <<= 1; t1 <<= 1; tN <<= 1; hpc <<= 1; hnc <<= 1; cc <<= 1;
+      };
+      if (!any_partial) {
+#pragma unroll 4
+        for (int c = 0; c < 32; ++c) column();
+      } else {
+        // some lane of the warp is in the partial final block of its last strip: everybody takes the
+        // per-column predicated loop for this one step instead of serialising two loops
+#pragma unroll 1
+        for (u32 c = 0; c < 32u; ++c)
+          if (c < run) column();
+      }
+      ++nblocks;
+      botacc += __popc(hpOut) - __popc(hnOut);
+      if (sl == (u32)L - 1u && s + 1u < S) stcg_u4(my_scratch + b, make_uint4(hpOut, hnOut, cOut, (u32)botacc));
+      if (b == sb1) {  // strip finished
+        if (islast) {
+          int acc = corner + tsum;
+#pragma unroll
+          for (int w = 0; w < W; ++w) {
+            const u32 kw = s * W + w;
+            u32 valid = 0;
+            if (kw < mwords) {
+              const u32 rem = m - 32u * kw;
+              valid = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+            }
+            acc += __popc(VP[w] & valid) - __popc(VN[w] & valid);
+          }
+          vfinal = acc;
+          fin_lane = true;
+        }
+        if (s + (u32)L < S) T0 += (u32)L + round_gap(r);
+        ++r;
+        s += (u32)L;
+        need_setup = s < S;
+      }
+    }
+    if (active) ++t;
+    __syncwarp();   // orders this step's scratch writes before later steps' reads
+    const u32 fin = __ballot_sync(0xffffffffu, fin_lane) & gmask;
+    if (in_group && fin) {  // uniform inside a group
+      const int v = __shfl_sync(gmask, vfinal, __ffs(fin) - 1);
+      if ((u32)v <= k) {
+        if (sl == 0) out[oidx] = v;
+        active = false;
+      } else {
+        // d > k proven; v is an upper bound of d
+        const u32 k3 = k > 0x55555555u ? 0xffffffffu : 3u * k;
+        set_band((u32)v < k3 ? (u32)v : k3);
+        start_attempt();
+        if (sl == 0) ++nretry;
+      }
+    }
+  }
+  if (stats) {
+    unsigned long long wb = (unsigned long long)nblocks * W;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      wb += __shfl_xor_sync(0xffffffffu, wb, o);
+      nretry += __shfl_xor_sync(0xffffffffu, nretry, o);
+      npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&stats[0], wb);
+      if (nretry) atomicAdd(&stats[1], (unsigned long long)nretry);
+      atomicAdd(&stats[2], (unsigned long long)npairs);
+    }
+  }
+}
+
+}  // namespace trpa

@@ -1,9 +1,10 @@
 // Instantiations + shape dispatch of the bit-vector edit-distance kernels (myers2.cuh: persistent,
 // shared-memory equality tables; myers.cuh: first-generation kernel kept for A/B runs with
 // TRPA_MYERS_V1=1).
+#include <algorithm>
 #include <cstdlib>
 
-#include "myers2.cuh"
+#include "myers3.cuh"
 #include "shapes.h"
 #include "launch.h"
 
@@ -80,6 +81,134 @@ cudaError_t launch_myers(int shape, const PairDesc* pairs, u32 count, const SeqD
   if (shape_hasn(shape))
     return launch_w<true>(widx, pairs, count, seqs, planes, nplane, out, L, scratch, scratch_stride, bucket, cursor, stream);
   return launch_w<false>(widx, pairs, count, seqs, planes, nplane, out, L, scratch, scratch_stride, bucket, cursor, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Banded path (myers3.cuh): per-round planning + launch.
+
+// One warp per pair: (1) upper bound of the distance from the ungapped (Hamming) alignment of the
+// pattern against the text prefix (+ the length difference), combined with the state machine's hint
+// (PairDesc.pad on entry, 0 = none) -> initial threshold k0; (2) shape: the lanes evaluate the 48
+// (W, L) candidates in parallel and keep the one minimising  cost * pairs-per-lane + time  (lane-time
+// when pairs are plentiful, latency when they are scarce).  pad <- shape | k0 << 8; histogram.
+__global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const SeqDesc* __restrict__ descs,
+                            const uint2* __restrict__ planes, const u32* __restrict__ nplane,
+                            u32* __restrict__ hist, u32 lanes_total, int band) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 p = warp; p < n_pairs; p += nwarps) {
+    const PairDesc pd = pairs[p];
+    const SeqDesc A = descs[pd.a], B = descs[pd.b];
+    u32 m, n, pw, tw;
+    if (A.len < B.len) { m = A.len; pw = A.woff; n = B.len; tw = B.woff; }
+    else               { m = B.len; pw = B.woff; n = A.len; tw = A.woff; }
+    const int hasn = (int)((A.flags | B.flags) & 1u);
+    u32 k0 = kPadKFull;
+    if (band && m >= 64u) {
+      const u32 mwords = (m + 31) >> 5;
+      u32 h = 0;
+      for (u32 w = lane; w < mwords; w += 32) {
+        const uint2 x = planes[pw + w], y = planes[tw + w];
+        u32 mm = (x.x ^ y.x) | (x.y ^ y.y);
+        if (hasn) mm |= nplane[pw + w] ^ nplane[tw + w];
+        if (w == mwords - 1 && (m & 31u)) mm &= (1u << (m & 31u)) - 1u;
+        h += __popc(mm);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+      u32 ub = h + (n - m);                       // a valid alignment: d <= ub
+      const u32 hint = pd.pad;
+      if (hint) {
+        const u32 hk = hint + (hint >> 3) + 32u;  // estimate, not a bound: the kernel verifies
+        if (hk < ub) ub = hk;
+      }
+      if (band > 1) ub = (u32)band;               // test hook: forced initial threshold
+      k0 = ub < kPadKFull ? ub : kPadKFull - 1u;
+    }
+    const BandGeom g = band_from_k(m ? m : 1u, n ? n : 1u, k0 >= kPadKFull ? 0xffffffffu : k0, !band);
+    uint64_t key = ~0ull;
+    int best = 0;
+    for (int id = (int)lane; id < kNumW * kNumL; id += 32) {
+      const ShapeCost sc = band_shape_cost(g, id % kNumW, id / kNumW);
+      const uint64_t kk = sc.cost * n_pairs + sc.time * lanes_total;
+      if (kk < key) { key = kk; best = id; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint64_t ok = __shfl_xor_sync(0xffffffffu, key, o);
+      const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+      if (ok < key || (ok == key && ob < best)) { key = ok; best = ob; }
+    }
+    if (lane == 0) {
+      const int shape = shape_id(best % kNumW, best / kNumW, hasn);
+      pairs[p].pad = (k0 << 8) | (u32)shape;
+      atomicAdd(&hist[shape], 1u);
+    }
+  }
+}
+
+cudaError_t launch_plan(PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, const uint2* planes, const u32* nplane,
+                        u32* hist, u32 lanes_total, int band, cudaStream_t stream) {
+  if (n_pairs == 0) return cudaSuccess;
+  const u32 blocks = std::min<u32>((n_pairs + 3) / 4, 148u * 16u);
+  plan_kernel<<<blocks, 128, 0, stream>>>(pairs, n_pairs, descs, planes, nplane, hist, lanes_total, band);
+  return cudaGetLastError();
+}
+
+template <int W, bool HASN>
+static cudaError_t launch_one3(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint2* planes,
+                               const u32* nplane, int* out, int L, uint4* scratch, u32 scratch_stride,
+                               u32* cursor, unsigned long long* stats, int force_full, u32* slots_out,
+                               cudaStream_t stream) {
+  typedef Myers2Cfg<W, HASN> Cfg;
+  static int occ = 0;
+  if (occ == 0) {
+    cudaError_t e = cudaFuncSetAttribute(myers3_kernel<W, HASN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, myers3_kernel<W, HASN>, 128, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    if (g_num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+      if (g_num_sms <= 0) g_num_sms = 148;
+    }
+  }
+  const u32 G = 32 / L;
+  const u32 warps = (count + G - 1) / G;
+  u32 blocks = (warps + 3) / 4;
+  const u32 resident = (u32)g_num_sms * (u32)occ;
+  if (blocks > resident) blocks = resident;
+  if (slots_out) { *slots_out = blocks * 4 * G; return cudaSuccess; }
+  myers3_kernel<W, HASN><<<blocks, 128, Cfg::kSmemBytes, stream>>>(pairs, count, seqs, planes, nplane, out, L, scratch,
+                                                                  scratch_stride, nullptr, cursor, stats, force_full);
+  return cudaGetLastError();
+}
+
+// slots_out != nullptr: only report the number of group slots (scratch lines) the launch would use
+cudaError_t launch_myers3(int shape, const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint2* planes,
+                          const u32* nplane, int* out, uint4* scratch, u32 scratch_stride, u32* cursor,
+                          unsigned long long* stats, int force_full, u32* slots_out, cudaStream_t stream) {
+  if (count == 0) { if (slots_out) *slots_out = 0; return cudaSuccess; }
+  const int L = 1 << shape_lidx(shape);
+  const bool hasn = shape_hasn(shape) != 0;
+#define TRPA_CASE3(I, WV)                                                                                          \
+  case I:                                                                                                          \
+    return hasn ? launch_one3<WV, true>(pairs, count, seqs, planes, nplane, out, L, scratch, scratch_stride, cursor, \
+                                        stats, force_full, slots_out, stream)                                      \
+                : launch_one3<WV, false>(pairs, count, seqs, planes, nplane, out, L, scratch, scratch_stride, cursor, \
+                                         stats, force_full, slots_out, stream);
+  switch (shape_widx(shape)) {
+    TRPA_CASE3(0, 1) TRPA_CASE3(1, 2) TRPA_CASE3(2, 4) TRPA_CASE3(3, 8) TRPA_CASE3(4, 12) TRPA_CASE3(5, 16) TRPA_CASE3(6, 20)
+    default:
+      return hasn ? launch_one3<24, true>(pairs, count, seqs, planes, nplane, out, L, scratch, scratch_stride, cursor,
+                                          stats, force_full, slots_out, stream)
+                  : launch_one3<24, false>(pairs, count, seqs, planes, nplane, out, L, scratch, scratch_stride, cursor,
+                                           stats, force_full, slots_out, stream);
+  }
+#undef TRPA_CASE3
 }
 
 }  // namespace trpa

@@ -71,4 +71,64 @@ TRPA_HD int lmin_for(uint32_t n_pairs, uint32_t lanes) {
   return l;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Banded kernel (myers3.cuh): geometry + cost model used to pick (W, L) per pair.
+// a = half band width below the main diagonal, ua = delta + a (above); see myers3.cuh.
+struct BandGeom {
+  uint32_t m, n, a, ua;
+  uint32_t k;   // effective threshold; 0xffffffff when the band covers the whole matrix
+  TRPA_HD uint32_t b0(uint32_t s, uint32_t R) const { const uint32_t x = s * R; return x > a ? (x - a) >> 5 : 0u; }
+  TRPA_HD uint32_t b1(uint32_t s, uint32_t R) const {
+    const uint32_t hi = (s + 1u) * R - 1u + ua;
+    return (hi < n - 1u ? hi : n - 1u) >> 5;
+  }
+};
+
+// threshold k -> band (m <= n).  The half width is at least 32 so that consecutive strips always
+// share a block; k = n is always sufficient (d <= n); patterns shorter than 64 are never banded.
+TRPA_HD BandGeom band_from_k(uint32_t m, uint32_t n, uint32_t k, bool force_full = false) {
+  BandGeom g;
+  const uint32_t delta = n - m;
+  g.m = m; g.n = n;
+  if (k < delta + 64u) k = delta + 64u;
+  if (k > n) k = n;
+  if (force_full || k < delta + 64u) { g.a = m; g.ua = n; g.k = 0xffffffffu; return g; }
+  g.a = (k - delta) >> 1; g.ua = delta + g.a; g.k = k;
+  return g;
+}
+
+// Group steps the rotating schedule needs for one attempt (gap evaluated at both ends of a round).
+TRPA_HD uint64_t band_steps(const BandGeom& g, int W, int L) {
+  const uint32_t R = 32u * (uint32_t)W;
+  const uint32_t mwords = (g.m + 31u) >> 5, nblk = (g.n + 31u) >> 5;
+  const uint32_t S = (mwords + W - 1) / W;
+  uint64_t off = 0;
+  for (uint32_t s0 = 0; s0 + L < S; s0 += L) {
+    int gap = 1;
+    const uint32_t l_hi = (S - L - 1u - s0) < (uint32_t)(L - 1) ? (S - L - 1u - s0) : (uint32_t)(L - 1);
+    const int t0 = (int)g.b1(s0, R) - (int)g.b0(s0 + L, R) + 1 - L;
+    const int t1 = (int)g.b1(s0 + l_hi, R) - (int)g.b0(s0 + l_hi + L, R) + 1 - L;
+    if (t0 > gap) gap = t0;
+    if (t1 > gap) gap = t1;
+    off += (uint64_t)L + (uint64_t)gap;
+  }
+  return off + ((S - 1u) % (uint32_t)L) + nblk;
+}
+
+// alu-pipe instructions of one lane-step: 32 columns x (10.4 per word + 14 per column) + the per-step
+// bookkeeping (boundary hand-over, schedule); strip set-up (equality table) per strip
+TRPA_HD uint64_t band_step_ops(int W) { return 32ull * (104ull * (uint64_t)W + 140ull) / 10ull + 150ull; }
+TRPA_HD uint64_t band_setup_ops(int W) { return 120ull + 25ull * (uint64_t)W; }
+
+struct ShapeCost { uint64_t time, cost; };   // time: alu instructions on the critical lane; cost = time * L
+TRPA_HD ShapeCost band_shape_cost(const BandGeom& g, int widx, int lidx) {
+  const int W = shape_W(widx), L = 1 << lidx;
+  const uint32_t mwords = (g.m + 31u) >> 5;
+  const uint32_t S = (mwords + W - 1) / W;
+  ShapeCost c;
+  c.time = band_steps(g, W, L) * band_step_ops(W) + (uint64_t)((S + L - 1) / L) * band_setup_ops(W);
+  c.cost = c.time * (uint64_t)L;
+  return c;
+}
+
 }  // namespace trpa

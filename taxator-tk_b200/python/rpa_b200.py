@@ -27,14 +27,14 @@ class Profile(ctypes.Structure):
                 ("ms_stage", ctypes.c_double), ("launches_stage", ctypes.c_uint64), ("bytes_stage", ctypes.c_uint64),
                 ("ms_decide", ctypes.c_double), ("launches_decide", ctypes.c_uint64),
                 ("ms_other", ctypes.c_double), ("launches_other", ctypes.c_uint64),
-                ("rounds", ctypes.c_uint64), ("pairs", ctypes.c_uint64)]
+                ("rounds", ctypes.c_uint64), ("pairs", ctypes.c_uint64), ("band_retries", ctypes.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 EXPORTS = ["trpa_abi_version", "trpa_last_error", "trpa_create", "trpa_destroy", "trpa_set_params",
-           "trpa_set_arena_bytes", "trpa_set_lookahead", "trpa_profile_reset", "trpa_profile_get", "trpa_load_taxonomy", "trpa_load_store",
+           "trpa_set_arena_bytes", "trpa_set_lookahead", "trpa_set_band", "trpa_set_tuning", "trpa_profile_reset", "trpa_profile_get", "trpa_load_taxonomy", "trpa_load_store",
            "trpa_predict_batch", "trpa_batch_upload", "trpa_batch_run", "trpa_batch_download",
            "trpa_edit_distance_batch", "trpa_protein_align_batch", "trpa_fetch_segments", "trpa_lca_batch",
            "trpa_int_alu_peak"]
@@ -96,6 +96,12 @@ class Context:
 
     def set_arena_bytes(self, nbytes):
         self._ck(self.L.trpa_set_arena_bytes(self.h, ctypes.c_uint64(int(nbytes))))
+
+    def set_band(self, on):
+        self._ck(self.L.trpa_set_band(self.h, ctypes.c_int(int(on))))
+
+    def set_tuning(self, key, value):
+        self._ck(self.L.trpa_set_tuning(self.h, ctypes.c_char_p(key.encode()), ctypes.c_int64(int(value))))
 
     def set_lookahead(self, k):
         self._ck(self.L.trpa_set_lookahead(self.h, int(k)))

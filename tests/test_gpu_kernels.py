@@ -115,3 +115,72 @@ def test_protein_align(ctx):
         cb = ol.codes_of(np.frombuffer(seqs[pb[k]], np.uint8), True)
         O.orc_protein_align(ol.ptr(ca, ol.u8p), len(ca), ol.ptr(cb, ol.u8p), len(cb), out6)
         assert got[k].tolist() == [out6[0], out6[1], out6[2]], (k, len(ca), len(cb), got[k].tolist(), list(out6))
+
+
+def _band_cases(rng, alpha, n_pairs, lens, rates):
+    seqs, pa, pb = [], [], []
+    for _ in range(n_pairs):
+        L = int(rng.choice(lens))
+        a = alpha[rng.integers(0, len(alpha), L)].tobytes()
+        b = _mutate(rng, a, float(rng.choice(rates)), alpha)
+        if rng.random() < 0.15:   # one side much longer / shorter
+            b = b + alpha[rng.integers(0, len(alpha), int(rng.integers(0, 400)))].tobytes()
+        if rng.random() < 0.1:
+            b = b[int(rng.integers(0, max(1, len(b) // 3))):]
+        seqs += [a, b]
+        pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)
+    return seqs, pa, pb
+
+
+@pytest.mark.parametrize("with_n", [False, True])
+def test_band_equals_full_matrix(ctx, with_n):
+    """Ukkonen band + verify/widen loop returns the same integers as the full DP matrix and the oracle,
+    for every (W, L) shape the planner can pick (plan_lanes moves it between lane-time and latency
+    mode) and for initial thresholds that are far too small (band_k0 forces retries)."""
+    rng = np.random.default_rng(23 + with_n)
+    alpha = np.frombuffer(b"ACGTN" if with_n else b"ACGT", np.uint8)
+    seqs, pa, pb = _band_cases(rng, alpha, 400, [40, 64, 65, 200, 700, 1500, 3000, 6000], [0.0, 0.01, 0.05, 0.15, 0.4, 0.9])
+    chars, off, ln = _table(seqs)
+    want = np.array([_oracle_ed(seqs[a], seqs[b]) for a, b in zip(pa, pb)], np.int32)
+    try:
+        ctx.set_band(0)
+        ctx.profile_reset()
+        full, _ = ctx.edit_distance_batch(chars, off, ln, pa, pb)
+        cells_full = ctx.profile()["cells_edit_distance"]
+        assert np.array_equal(full, want), np.flatnonzero(full != want)[:10]
+        ctx.set_band(1)
+        for lanes in (0, 32, 1 << 24):
+            for k0 in (0, 64, 300):
+                ctx.set_tuning("plan_lanes", lanes)
+                ctx.set_tuning("band_k0", k0)
+                ctx.profile_reset()
+                got, _ = ctx.edit_distance_batch(chars, off, ln, pa, pb)
+                prof = ctx.profile()
+                assert np.array_equal(got, want), (lanes, k0, np.flatnonzero(got != want)[:10])
+                if k0 == 0:
+                    assert prof["band_retries"] == 0          # the planned threshold is a true upper bound
+                    assert prof["cells_edit_distance"] < cells_full
+                else:
+                    assert prof["band_retries"] > 0
+    finally:
+        ctx.set_band(1)
+        ctx.set_tuning("plan_lanes", 0)
+        ctx.set_tuning("band_k0", 0)
+
+
+def test_band_long_pairs(ctx):
+    """Long noisy pairs (the 10-50 kb regime): band with indels, several strips per lane."""
+    rng = np.random.default_rng(31)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    seqs, pa, pb = _band_cases(rng, alpha, 24, [10000, 20000, 33000, 50000], [0.02, 0.15, 0.3])
+    chars, off, ln = _table(seqs)
+    want = np.array([_oracle_ed(seqs[a], seqs[b]) for a, b in zip(pa, pb)], np.int32)
+    try:
+        for lanes, k0 in ((0, 0), (1 << 24, 0), (1 << 24, 500), (0, 2000)):
+            ctx.set_tuning("plan_lanes", lanes)
+            ctx.set_tuning("band_k0", k0)
+            got, _ = ctx.edit_distance_batch(chars, off, ln, pa, pb)
+            assert np.array_equal(got, want), (lanes, k0, np.flatnonzero(got != want)[:10])
+    finally:
+        ctx.set_tuning("plan_lanes", 0)
+        ctx.set_tuning("band_k0", 0)

@@ -4,6 +4,7 @@
 // There is no CPU fallback: every compute entry point needs a CUDA device.
 // Compile with --fmad=false (decision arithmetic must match the reference's IEEE float/double ops).
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -128,6 +129,10 @@ struct trpa_ctx {
   DevBuf<int2> scratch_aa;
   int band = 1;               // 1: Ukkonen band (exact), 0: full DP matrix
   int myers_version = 3;      // 3: banded rotating-strip kernel, 2: myers2 (A/B runs, TRPA_MYERS=2)
+  static constexpr int kAux = 6;   // shape buckets of a round run concurrently on these streams
+  cudaStream_t aux[kAux] = {};
+  cudaEvent_t aux_done[kAux] = {};
+  cudaEvent_t fork_ev = nullptr;
   u32 band_k0 = 0;            // test hook: forced initial threshold (0 = planned), exercises the retry loop
   u32 plan_lanes = 0;         // test hook: lanes the shape planner assumes (0 = num_sms * 16 warps * 32)
   u32* h_counters = nullptr;  // pinned: kNumCounters round counters + kNumShapes shape histogram
@@ -295,30 +300,74 @@ static int launch_myers_shapes3(trpa_ctx* c, const u32* h_hist, const PairDesc* 
                                 const uint2* planes, const u32* nplane, int* out, u32 max_len) {
   const u32 stride = (max_len + 31) / 32 + 1;
   CK(cudaMemsetAsync(c->d_hist.p + 2 * kNumShapes, 0, sizeof(u32) * kNumShapes, c->stream));
-  u32 max_slots = 0;
-  for (int shape = 0; shape < kNumShapes; ++shape) {
-    if (!h_hist[shape]) continue;
-    u32 slots = 0;
-    CK(launch_myers3(shape, nullptr, h_hist[shape], nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, &slots, c->stream));
-    max_slots = std::max(max_slots, slots);
-  }
-  // kernels of one stream run back to back, so one scratch area serves all shapes
-  if (c->scratch3.ensure((size_t)max_slots * stride + 1)) return TRPA_ERR_NOMEM;
-  static const bool debug = getenv("TRPA_DEBUG") != nullptr;
-  if (debug) {
-    fprintf(stderr, "[trpa] myers3 round:");
-    for (int shape = 0; shape < kNumShapes; ++shape)
-      if (h_hist[shape]) fprintf(stderr, " W%dxL%d%s:%u", shape_W(shape_widx(shape)), 1 << shape_lidx(shape), shape_hasn(shape) ? "N" : "", h_hist[shape]);
-    fprintf(stderr, "\n");
-  }
+  // every shape bucket is one persistent launch; the buckets run concurrently (own stream, own
+  // scratch region) so that the tail of one bucket overlaps the others
+  struct Job { int shape; u32 start, cnt, slots; size_t scr; };
+  Job jobs[kNumShapes];
+  int nj = 0;
   u32 start = 0;
+  size_t scr_total = 0;
   for (int shape = 0; shape < kNumShapes; ++shape) {
     const u32 cnt = h_hist[shape];
     if (!cnt) continue;
-    CK(launch_myers3(shape, sorted + start, cnt, descs, planes, nplane, out, c->scratch3.p, stride,
-                     c->d_hist.p + 2 * kNumShapes + shape, c->d_plan.p + 1, c->band ? 0 : 1, nullptr, c->stream));
-    c->prof.launches_edit_distance++;
+    u32 slots = 0;
+    CK(launch_myers3(shape, nullptr, cnt, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, &slots, c->stream));
+    jobs[nj++] = Job{shape, start, cnt, slots, scr_total};
+    scr_total += (size_t)slots * stride;
     start += cnt;
+  }
+  if (c->scratch3.ensure(scr_total + 1)) return TRPA_ERR_NOMEM;
+  static const bool debug = getenv("TRPA_DEBUG") != nullptr;
+  if (debug) {
+    fprintf(stderr, "[trpa] myers3 round:");
+    for (int j = 0; j < nj; ++j)
+      fprintf(stderr, " W%dxL%d%s:%u", shape_W(shape_widx(jobs[j].shape)), 1 << shape_lidx(jobs[j].shape),
+              shape_hasn(jobs[j].shape) ? "N" : "", jobs[j].cnt);
+    fprintf(stderr, "\n");
+  }
+  // largest buckets first
+  std::sort(jobs, jobs + nj, [](const Job& x, const Job& y) { return x.cnt > y.cnt; });
+  const bool fork = nj > 1;
+  if (fork) {
+    if (!c->fork_ev) {
+      CK(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+      for (int i = 0; i < trpa_ctx::kAux; ++i) {
+        CK(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->aux_done[i], cudaEventDisableTiming));
+      }
+    }
+    CK(cudaEventRecord(c->fork_ev, c->stream));
+  }
+  int used = 0;
+  for (int j = 0; j < nj; ++j) {
+    cudaStream_t st = c->stream;
+    if (fork && j > 0) {
+      const int a = (j - 1) % trpa_ctx::kAux;
+      st = c->aux[a];
+      if (a >= used) { CK(cudaStreamWaitEvent(st, c->fork_ev, 0)); used = a + 1; }
+    }
+    CK(launch_myers3(jobs[j].shape, sorted + jobs[j].start, jobs[j].cnt, descs, planes, nplane, out,
+                     c->scratch3.p + jobs[j].scr, stride, c->d_hist.p + 2 * kNumShapes + jobs[j].shape, c->d_plan.p + 1,
+                     c->band ? 0 : 1, nullptr, st));
+    c->prof.launches_edit_distance++;
+  }
+  for (int a = 0; a < used; ++a) {
+    CK(cudaEventRecord(c->aux_done[a], c->aux[a]));
+    CK(cudaStreamWaitEvent(c->stream, c->aux_done[a], 0));
+  }
+  if (debug) {   // per-round device time and executed cells (debug only: adds a sync)
+    static cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (!e0) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+    unsigned long long h0[3], h1[3];
+    cudaStreamSynchronize(c->stream);
+    cudaMemcpy(h1, c->d_plan.p + 1, sizeof(h1), cudaMemcpyDeviceToHost);
+    static unsigned long long last[3] = {0, 0, 0};
+    for (int i = 0; i < 3; ++i) { h0[i] = h1[i] >= last[i] ? h1[i] - last[i] : h1[i]; last[i] = h1[i]; }
+    static auto t_last = std::chrono::steady_clock::now();
+    const auto t_now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[trpa]   executed %.3g cells, %llu retries, %llu pairs, %.3f ms since previous round\n",
+            (double)h0[0] * 1024.0, h0[1], h0[2], std::chrono::duration<double, std::milli>(t_now - t_last).count());
+    t_last = t_now;
   }
   return 0;
 }
@@ -381,6 +430,10 @@ void trpa_destroy(trpa_ctx* c) {
   c->d_buckets.release(); c->arena_planes.release(); c->arena_n.release(); c->arena_aa.release();
   c->scratch.release(); c->scratch_aa.release(); c->scratch3.release(); c->d_plan.release();
   for (auto& e : c->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  if (c->fork_ev) {
+    cudaEventDestroy(c->fork_ev);
+    for (int i = 0; i < trpa_ctx::kAux; ++i) { cudaStreamDestroy(c->aux[i]); cudaEventDestroy(c->aux_done[i]); }
+  }
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;

@@ -488,7 +488,9 @@ def generate_fast(cfg: SynthConfig, block: int = 100) -> SynthData:
     b1 = b0 + (Lq // block)[:, None]
     ident = cum[g0[:, None], oi, b1] - cum[g0[:, None], oi, b0]   # (nq, K) exact block sums
     ident = np.where(valid, ident, (Lq[:, None] * 0.5).astype(np.int64))
-    ident = np.round(ident * (1.0 - cfg.query_sub)).astype(np.int64)
+    # what an aligner would report: matches shrink with the query's substitutions and deletions,
+    # the alignment grows by the query's insertions (alnlen - identities ~ edit operations)
+    ident = np.round(ident * (1.0 - cfg.query_sub) * (1.0 - cfg.query_indel / 2)).astype(np.int64)
     # partial records
     part = rng.random((nq, K)) < cfg.frac_partial
     a = (rng.random((nq, K)) * (Lq[:, None] // 4)).astype(np.int64) * part
@@ -497,6 +499,8 @@ def generate_fast(cfg: SynthConfig, block: int = 100) -> SynthData:
     qe = Lq[:, None] - b
     alnlen = qe - qs + 1
     ident = np.minimum((ident * alnlen) // Lq[:, None], alnlen - 1)
+    if cfg.query_indel > 0:
+        alnlen = np.round(alnlen * (1.0 + cfg.query_indel / 2)).astype(np.int64)
     # strictly decreasing identities per query (tie-free (score, identities))
     srt = np.argsort(-ident, axis=1, kind="stable")
     ident_s = np.take_along_axis(ident, srt, axis=1)

@@ -377,6 +377,7 @@ def main():
         "gpu_launches": int(prof["launches_edit_distance"] + prof["launches_protein"] + prof["launches_stage"] +
                             prof["launches_decide"] + prof["launches_other"]),
         "rounds_per_step": prof["rounds"] / args.steps,
+        "pairs_launched_per_step": prof["pairs"] / args.steps,
         "phase_ms_per_step": {"align": k_ms / args.steps, "stage": prof["ms_stage"] / args.steps,
                               "decide": prof["ms_decide"] / args.steps, "bucket": prof["ms_other"] / args.steps},
         "clocks": clocks,

@@ -81,6 +81,39 @@ struct Store {
 
 struct EventPair { cudaEvent_t a, b; int kind; };
 
+// One sub-batch pipeline: its own stream, round queues' counters, shape histogram / work cursors,
+// kernel scratch and timing events.  A batch is cut into chunks of segments; the pipes of a context
+// work on different chunks at the same time, so that the tail of one chunk's alignment kernels, its
+// small decide / plan kernels and its host round trips overlap another chunk's alignments.
+struct Pipe {
+  static constexpr int kAux = 6;   // shape buckets of a round run concurrently on these streams
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  bool ready = false;
+  DevBuf<u32> d_counters;
+  DevBuf<u32> d_hist;         // kNumShapes counts + scatter cursors + kernel work cursors
+  DevBuf<uint2> d_buckets;    // kNumShapes {start,count}
+  DevBuf<u32> scratch;
+  DevBuf<uint4> scratch3;     // banded kernel: wrap-around strip boundaries, one line per group slot
+  DevBuf<unsigned long long> d_plan;  // [1..3] {word-blocks, retries, pairs} of myers3
+  DevBuf<int2> scratch_aa;
+  cudaStream_t aux[kAux] = {};
+  cudaEvent_t aux_done[kAux] = {};
+  cudaEvent_t fork_ev = nullptr;
+  u32* h_counters = nullptr;  // pinned: kNumCounters round counters + kNumShapes shape histogram
+  std::vector<EventPair> ev_pool;
+  size_t ev_used = 0;
+  // run state of trpa_batch_run
+  int state = 0;
+  u32 sb = 0, se = 0, n_pairs = 0;
+  PairDesc* pairs = nullptr;
+  PairDesc* sorted = nullptr;
+  Batch B;
+
+  int init(cudaStream_t user_stream);
+  void release();
+};
+
 }  // namespace trpa
 
 using namespace trpa;
@@ -100,6 +133,8 @@ struct trpa_ctx {
   std::vector<trpa_segment> h_segs;
   std::vector<trpa_candidate> h_cands;
   std::vector<u32> chunk_begin;  // segment index boundaries
+  std::vector<u64> chunk_qoff;   // start of the chunk's slice of the pair / stage queues
+  int run_pipes = 1;             // pipes the uploaded batch was planned for
   u32 n_segs = 0, n_cands = 0;
   u32 max_stage_len = 0;
   bool batch_ready = false;
@@ -116,31 +151,22 @@ struct trpa_ctx {
   DevBuf<SeqDesc> d_descs;
   DevBuf<PairDesc> d_pairs, d_pairs_sorted;
   DevBuf<StageReq> d_stage;
-  DevBuf<u32> d_counters;
-  DevBuf<u32> d_hist;         // kNumShapes counts + scatter cursors + kernel work cursors
-  DevBuf<uint2> d_buckets;    // kNumShapes {start,count}
   DevBuf<uint2> arena_planes;
   DevBuf<u32> arena_n;
   DevBuf<uint8_t> arena_aa;
   u64 arena_units = 0;
-  DevBuf<u32> scratch;
-  DevBuf<uint4> scratch3;     // banded kernel: wrap-around strip boundaries, one line per group slot
-  DevBuf<unsigned long long> d_plan;  // [1..3] {word-blocks, retries, pairs} of myers3
-  DevBuf<int2> scratch_aa;
   int band = 1;               // 1: Ukkonen band (exact), 0: full DP matrix
   int myers_version = 3;      // 3: banded rotating-strip kernel, 2: myers2 (A/B runs, TRPA_MYERS=2)
-  static constexpr int kAux = 6;   // shape buckets of a round run concurrently on these streams
-  cudaStream_t aux[kAux] = {};
-  cudaEvent_t aux_done[kAux] = {};
-  cudaEvent_t fork_ev = nullptr;
+  // pipes: independent sub-batch pipelines whose rounds overlap on the GPU (pipe[0] runs on `stream`)
+  static constexpr int kMaxPipes = 4;
+  Pipe pipe[kMaxPipes];
+  int n_pipes = 1;   // measured on C2: overlapping chunks gains nothing (the alignment kernels already saturate the GPU)
   u32 band_k0 = 0;            // test hook: forced initial threshold (0 = planned), exercises the retry loop
+  int force_shape = -1;       // tuning hook: (lidx * kNumW + widx) forced for every pair, -1 = planner
   u32 plan_lanes = 0;         // test hook: lanes the shape planner assumes (0 = num_sms * 16 warps * 32)
-  u32* h_counters = nullptr;  // pinned: kNumCounters round counters + kNumShapes shape histogram
   int num_sms = 148;
   // profiling
   trpa_profile prof;
-  std::vector<EventPair> ev_pool;
-  size_t ev_used = 0;
 };
 
 namespace trpa {
@@ -196,26 +222,26 @@ __global__ void lca_kernel(Taxonomy T, const u32* a, const u32* b, u32 n, u32* o
 }
 
 // ------------------------------------------------------------------------------------ helpers
-static int begin_event(trpa_ctx* c, int kind) {
-  if (c->ev_used == c->ev_pool.size()) {
+static int begin_event(Pipe& P, int kind) {
+  if (P.ev_used == P.ev_pool.size()) {
     EventPair e; e.kind = kind;
     if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return -1;
-    c->ev_pool.push_back(e);
+    P.ev_pool.push_back(e);
   }
-  c->ev_pool[c->ev_used].kind = kind;
-  cudaEventRecord(c->ev_pool[c->ev_used].a, c->stream);
-  return (int)c->ev_used++;
+  P.ev_pool[P.ev_used].kind = kind;
+  cudaEventRecord(P.ev_pool[P.ev_used].a, P.stream);
+  return (int)P.ev_used++;
 }
-static void end_event(trpa_ctx* c, int id) {
-  if (id >= 0) cudaEventRecord(c->ev_pool[id].b, c->stream);
+static void end_event(Pipe& P, int id) {
+  if (id >= 0) cudaEventRecord(P.ev_pool[id].b, P.stream);
 }
 enum { EV_MYERS = 0, EV_PROTEIN, EV_STAGE, EV_DECIDE, EV_OTHER };
 // call after a stream sync
-static void harvest_events(trpa_ctx* c) {
-  for (size_t i = 0; i < c->ev_used; ++i) {
+static void harvest_events(trpa_ctx* c, Pipe& P) {
+  for (size_t i = 0; i < P.ev_used; ++i) {
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, c->ev_pool[i].a, c->ev_pool[i].b) != cudaSuccess) { cudaGetLastError(); continue; }
-    switch (c->ev_pool[i].kind) {
+    if (cudaEventElapsedTime(&ms, P.ev_pool[i].a, P.ev_pool[i].b) != cudaSuccess) { cudaGetLastError(); continue; }
+    switch (P.ev_pool[i].kind) {
       case EV_MYERS: c->prof.ms_edit_distance += ms; break;
       case EV_PROTEIN: c->prof.ms_protein += ms; break;
       case EV_STAGE: c->prof.ms_stage += ms; break;
@@ -223,12 +249,44 @@ static void harvest_events(trpa_ctx* c) {
       default: c->prof.ms_other += ms; break;
     }
   }
-  c->ev_used = 0;
+  P.ev_used = 0;
 }
 
 static int use_device(trpa_ctx* c) {
   CK(cudaSetDevice(c->device));
   return 0;
+}
+
+int Pipe::init(cudaStream_t user_stream) {
+  if (ready) return 0;
+  if (user_stream) { stream = user_stream; own_stream = false; }
+  else {
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    own_stream = true;
+  }
+  CK(cudaMallocHost(&h_counters, sizeof(u32) * (kNumCounters + 2 * kNumShapes)));
+  if (d_counters.ensure(kNumCounters) || d_hist.ensure(3 * kNumShapes) || d_buckets.ensure(kNumShapes) || d_plan.ensure(4)) return TRPA_ERR_NOMEM;
+  CK(cudaMemsetAsync(d_plan.p, 0, 4 * sizeof(unsigned long long), stream));
+  CK(cudaStreamSynchronize(stream));
+  ready = true;
+  return 0;
+}
+void Pipe::release() {
+  if (stream) cudaStreamSynchronize(stream);
+  d_counters.release(); d_hist.release(); d_buckets.release(); scratch.release(); scratch3.release();
+  d_plan.release(); scratch_aa.release();
+  for (auto& e : ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  ev_pool.clear();
+  if (fork_ev) {
+    cudaEventDestroy(fork_ev);
+    for (int i = 0; i < kAux; ++i) { cudaStreamDestroy(aux[i]); cudaEventDestroy(aux_done[i]); }
+    fork_ev = nullptr;
+  }
+  if (h_counters) cudaFreeHost(h_counters);
+  h_counters = nullptr;
+  if (own_stream && stream) cudaStreamDestroy(stream);
+  stream = nullptr;
+  ready = false;
 }
 
 static Taxonomy dev_tax(trpa_ctx* c) { return Taxonomy{c->t_parent.p, c->t_left.p, c->t_right.p, c->t_depth.p, c->root}; }
@@ -237,25 +295,24 @@ static Taxonomy dev_tax(trpa_ctx* c) { return Taxonomy{c->t_parent.p, c->t_left.
 // bucket_pairs: exact kernel shape of every pair (length class, has-N, and -- when the round is too
 // small to fill the GPU -- more lanes per pair), counting sort by shape on the device; the per-shape
 // counts come back to the host (h_hist) so that only non-empty shapes are launched.
-static int bucket_pairs(trpa_ctx* c, PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, PairDesc* sorted, u32* h_hist) {
-  CK(cudaMemsetAsync(c->d_hist.p, 0, sizeof(u32) * 3 * kNumShapes, c->stream));
+static int bucket_pairs(trpa_ctx* c, Pipe& P, PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, PairDesc* sorted, u32* h_hist) {
+  CK(cudaMemsetAsync(P.d_hist.p, 0, sizeof(u32) * 3 * kNumShapes, P.stream));
   const u32 blocks = std::min<u32>((n_pairs + 255) / 256, 148 * 8);
   const int lmin = lmin_for(n_pairs, (u32)c->num_sms * 16u * 32u);
-  classify_kernel<<<blocks, 256, 0, c->stream>>>(pairs, n_pairs, descs, c->d_hist.p, lmin);
-  scan_kernel<<<1, 32, 0, c->stream>>>(c->d_hist.p, c->d_buckets.p);
-  scatter_kernel<<<blocks, 256, 0, c->stream>>>(pairs, n_pairs, c->d_hist.p, sorted);
+  classify_kernel<<<blocks, 256, 0, P.stream>>>(pairs, n_pairs, descs, P.d_hist.p, lmin);
+  scan_kernel<<<1, 32, 0, P.stream>>>(P.d_hist.p, P.d_buckets.p);
+  scatter_kernel<<<blocks, 256, 0, P.stream>>>(pairs, n_pairs, P.d_hist.p, sorted);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(h_hist, c->d_hist.p, sizeof(u32) * kNumShapes, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  return 0;
+  CK(cudaMemcpyAsync(h_hist, P.d_hist.p, sizeof(u32) * kNumShapes, cudaMemcpyDeviceToHost, P.stream));
+  return 0;   // asynchronous: synchronise P.stream before reading h_hist
 }
 
 // one launch per non-empty shape over the shape-sorted pair list
-static int launch_myers_shapes(trpa_ctx* c, const u32* h_hist, const PairDesc* sorted, const SeqDesc* descs,
+static int launch_myers_shapes(trpa_ctx* c, Pipe& P, const u32* h_hist, const PairDesc* sorted, const SeqDesc* descs,
                                const uint2* planes, const u32* nplane, int* out, u32 max_len) {
   const u32 stride = (max_len + 31) / 32 + 1;
   // work cursors of the persistent kernels (one per shape)
-  CK(cudaMemsetAsync(c->d_hist.p + 2 * kNumShapes, 0, sizeof(u32) * kNumShapes, c->stream));
+  CK(cudaMemsetAsync(P.d_hist.p + 2 * kNumShapes, 0, sizeof(u32) * kNumShapes, P.stream));
   u32 start = 0;
   for (int shape = 0; shape < kNumShapes; ++shape) {
     const u32 cnt = h_hist[shape];
@@ -265,11 +322,11 @@ static int launch_myers_shapes(trpa_ctx* c, const u32* h_hist, const PairDesc* s
     u32* scr = nullptr;
     if (L == 32 && (u64)stride * 32 > (u64)32 * W * 32) {  // some pattern may need >1 strip
       // kernels of one stream run back to back, so one scratch area serves all shapes
-      if (c->scratch.ensure((size_t)myers_group_slots(shape, cnt) * 3 * stride)) return TRPA_ERR_NOMEM;
-      scr = c->scratch.p;
+      if (P.scratch.ensure((size_t)myers_group_slots(shape, cnt) * 3 * stride)) return TRPA_ERR_NOMEM;
+      scr = P.scratch.p;
     }
     CK(launch_myers(shape, sorted + start, cnt, descs, planes, nplane, out, scr, stride, nullptr,
-                    c->d_hist.p + 2 * kNumShapes + shape, c->stream));
+                    P.d_hist.p + 2 * kNumShapes + shape, P.stream));
     c->prof.launches_edit_distance++;
     start += cnt;
   }
@@ -278,28 +335,23 @@ static int launch_myers_shapes(trpa_ctx* c, const u32* h_hist, const PairDesc* s
 
 
 // ---- banded path: plan (threshold + shape per pair), counting sort by shape, one launch per shape
-static int bucket_pairs3(trpa_ctx* c, PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, const uint2* planes,
+static int bucket_pairs3(trpa_ctx* c, Pipe& P, PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, const uint2* planes,
                          const u32* nplane, PairDesc* sorted, u32* h_hist) {
-  if (!c->d_plan.p) {
-    if (c->d_plan.ensure(4)) return TRPA_ERR_NOMEM;
-    CK(cudaMemsetAsync(c->d_plan.p, 0, 4 * sizeof(unsigned long long), c->stream));
-  }
-  CK(cudaMemsetAsync(c->d_hist.p, 0, sizeof(u32) * 3 * kNumShapes, c->stream));
+  CK(cudaMemsetAsync(P.d_hist.p, 0, sizeof(u32) * 3 * kNumShapes, P.stream));
   const u32 blocks = std::min<u32>((n_pairs + 255) / 256, 148 * 8);
-  CK(launch_plan(pairs, n_pairs, descs, planes, nplane, c->d_hist.p, c->plan_lanes ? c->plan_lanes : (u32)c->num_sms * 16u * 32u,
-                 c->band ? (c->band_k0 ? (int)c->band_k0 : 1) : 0, c->stream));
-  scan_kernel<<<1, 32, 0, c->stream>>>(c->d_hist.p, c->d_buckets.p);
-  scatter_kernel<<<blocks, 256, 0, c->stream>>>(pairs, n_pairs, c->d_hist.p, sorted);
+  CK(launch_plan(pairs, n_pairs, descs, planes, nplane, P.d_hist.p, c->plan_lanes ? c->plan_lanes : (u32)c->num_sms * 16u * 32u,
+                 c->band ? (c->band_k0 ? (int)c->band_k0 : 1) : 0, c->force_shape, P.stream));
+  scan_kernel<<<1, 32, 0, P.stream>>>(P.d_hist.p, P.d_buckets.p);
+  scatter_kernel<<<blocks, 256, 0, P.stream>>>(pairs, n_pairs, P.d_hist.p, sorted);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(h_hist, c->d_hist.p, sizeof(u32) * kNumShapes, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  return 0;
+  CK(cudaMemcpyAsync(h_hist, P.d_hist.p, sizeof(u32) * kNumShapes, cudaMemcpyDeviceToHost, P.stream));
+  return 0;   // asynchronous: synchronise P.stream before reading h_hist
 }
 
-static int launch_myers_shapes3(trpa_ctx* c, const u32* h_hist, const PairDesc* sorted, const SeqDesc* descs,
+static int launch_myers_shapes3(trpa_ctx* c, Pipe& P, const u32* h_hist, const PairDesc* sorted, const SeqDesc* descs,
                                 const uint2* planes, const u32* nplane, int* out, u32 max_len) {
   const u32 stride = (max_len + 31) / 32 + 1;
-  CK(cudaMemsetAsync(c->d_hist.p + 2 * kNumShapes, 0, sizeof(u32) * kNumShapes, c->stream));
+  CK(cudaMemsetAsync(P.d_hist.p + 2 * kNumShapes, 0, sizeof(u32) * kNumShapes, P.stream));
   // every shape bucket is one persistent launch; the buckets run concurrently (own stream, own
   // scratch region) so that the tail of one bucket overlaps the others
   struct Job { int shape; u32 start, cnt, slots; size_t scr; };
@@ -311,12 +363,12 @@ static int launch_myers_shapes3(trpa_ctx* c, const u32* h_hist, const PairDesc* 
     const u32 cnt = h_hist[shape];
     if (!cnt) continue;
     u32 slots = 0;
-    CK(launch_myers3(shape, nullptr, cnt, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, &slots, c->stream));
+    CK(launch_myers3(shape, nullptr, cnt, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, &slots, P.stream));
     jobs[nj++] = Job{shape, start, cnt, slots, scr_total};
     scr_total += (size_t)slots * stride;
     start += cnt;
   }
-  if (c->scratch3.ensure(scr_total + 1)) return TRPA_ERR_NOMEM;
+  if (P.scratch3.ensure(scr_total + 1)) return TRPA_ERR_NOMEM;
   static const bool debug = getenv("TRPA_DEBUG") != nullptr;
   if (debug) {
     fprintf(stderr, "[trpa] myers3 round:");
@@ -329,38 +381,38 @@ static int launch_myers_shapes3(trpa_ctx* c, const u32* h_hist, const PairDesc* 
   std::sort(jobs, jobs + nj, [](const Job& x, const Job& y) { return x.cnt > y.cnt; });
   const bool fork = nj > 1;
   if (fork) {
-    if (!c->fork_ev) {
-      CK(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
-      for (int i = 0; i < trpa_ctx::kAux; ++i) {
-        CK(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&c->aux_done[i], cudaEventDisableTiming));
+    if (!P.fork_ev) {
+      CK(cudaEventCreateWithFlags(&P.fork_ev, cudaEventDisableTiming));
+      for (int i = 0; i < Pipe::kAux; ++i) {
+        CK(cudaStreamCreateWithFlags(&P.aux[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&P.aux_done[i], cudaEventDisableTiming));
       }
     }
-    CK(cudaEventRecord(c->fork_ev, c->stream));
+    CK(cudaEventRecord(P.fork_ev, P.stream));
   }
   int used = 0;
   for (int j = 0; j < nj; ++j) {
-    cudaStream_t st = c->stream;
+    cudaStream_t st = P.stream;
     if (fork && j > 0) {
-      const int a = (j - 1) % trpa_ctx::kAux;
-      st = c->aux[a];
-      if (a >= used) { CK(cudaStreamWaitEvent(st, c->fork_ev, 0)); used = a + 1; }
+      const int a = (j - 1) % Pipe::kAux;
+      st = P.aux[a];
+      if (a >= used) { CK(cudaStreamWaitEvent(st, P.fork_ev, 0)); used = a + 1; }
     }
     CK(launch_myers3(jobs[j].shape, sorted + jobs[j].start, jobs[j].cnt, descs, planes, nplane, out,
-                     c->scratch3.p + jobs[j].scr, stride, c->d_hist.p + 2 * kNumShapes + jobs[j].shape, c->d_plan.p + 1,
+                     P.scratch3.p + jobs[j].scr, stride, P.d_hist.p + 2 * kNumShapes + jobs[j].shape, P.d_plan.p + 1,
                      c->band ? 0 : 1, nullptr, st));
     c->prof.launches_edit_distance++;
   }
   for (int a = 0; a < used; ++a) {
-    CK(cudaEventRecord(c->aux_done[a], c->aux[a]));
-    CK(cudaStreamWaitEvent(c->stream, c->aux_done[a], 0));
+    CK(cudaEventRecord(P.aux_done[a], P.aux[a]));
+    CK(cudaStreamWaitEvent(P.stream, P.aux_done[a], 0));
   }
   if (debug) {   // per-round device time and executed cells (debug only: adds a sync)
     static cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (!e0) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
     unsigned long long h0[3], h1[3];
-    cudaStreamSynchronize(c->stream);
-    cudaMemcpy(h1, c->d_plan.p + 1, sizeof(h1), cudaMemcpyDeviceToHost);
+    cudaStreamSynchronize(P.stream);
+    cudaMemcpy(h1, P.d_plan.p + 1, sizeof(h1), cudaMemcpyDeviceToHost);
     static unsigned long long last[3] = {0, 0, 0};
     for (int i = 0; i < 3; ++i) { h0[i] = h1[i] >= last[i] ? h1[i] - last[i] : h1[i]; last[i] = h1[i]; }
     static auto t_last = std::chrono::steady_clock::now();
@@ -373,12 +425,12 @@ static int launch_myers_shapes3(trpa_ctx* c, const u32* h_hist, const PairDesc* 
 }
 
 // {word-blocks, retries, pairs} of the banded kernel since the last call -> profile
-static int harvest_band_stats(trpa_ctx* c) {
-  if (!c->d_plan.p) return 0;
+static int harvest_band_stats(trpa_ctx* c, Pipe& P) {
+  if (!P.d_plan.p) return 0;
   unsigned long long h[3] = {0, 0, 0};
-  CK(cudaMemcpyAsync(h, c->d_plan.p + 1, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  CK(cudaMemsetAsync(c->d_plan.p + 1, 0, sizeof(h), c->stream));
+  CK(cudaMemcpyAsync(h, P.d_plan.p + 1, sizeof(h), cudaMemcpyDeviceToHost, P.stream));
+  CK(cudaStreamSynchronize(P.stream));
+  CK(cudaMemsetAsync(P.d_plan.p + 1, 0, sizeof(h), P.stream));
   c->prof.cells_edit_distance += h[0] * 1024ull;
   c->prof.band_retries += h[1];
   return 0;
@@ -405,15 +457,13 @@ trpa_ctx* trpa_create(int device, void* cuda_stream) {
   trpa_ctx* c = new trpa_ctx();
   c->device = device;
   memset(&c->prof, 0, sizeof(c->prof));
-  if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
-  else {
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete c; return nullptr; }
-    c->own_stream = true;
-  }
-  if (cudaMallocHost(&c->h_counters, sizeof(u32) * (kNumCounters + 2 * kNumShapes)) != cudaSuccess) { set_error("cudaMallocHost failed"); delete c; return nullptr; }
+  if (c->pipe[0].init((cudaStream_t)cuda_stream)) { delete c; return nullptr; }
+  c->stream = c->pipe[0].stream;
+  c->own_stream = false;   // owned by pipe[0]
   if (cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->num_sms <= 0) c->num_sms = 148;
   if (const char* e = getenv("TRPA_BAND")) c->band = e[0] != '0';
   if (const char* e = getenv("TRPA_MYERS")) c->myers_version = e[0] == '2' ? 2 : 3;
+  if (const char* e = getenv("TRPA_PIPES")) c->n_pipes = std::max(1, std::min((int)trpa_ctx::kMaxPipes, atoi(e)));
   return c;
 }
 
@@ -426,16 +476,9 @@ void trpa_destroy(trpa_ctx* c) {
   c->d_segs.release(); c->d_cands.release(); c->d_results.release(); c->d_state.release();
   c->d_qd.release(); c->d_qsim.release(); c->d_bf_d.release(); c->d_cflags.release(); c->d_og_i.release(); c->d_tag.release();
   c->d_bf_node.release(); c->d_og_d.release(); c->d_res.release(); c->d_descs.release(); c->d_pairs.release();
-  c->d_pairs_sorted.release(); c->d_stage.release(); c->d_counters.release(); c->d_hist.release();
-  c->d_buckets.release(); c->arena_planes.release(); c->arena_n.release(); c->arena_aa.release();
-  c->scratch.release(); c->scratch_aa.release(); c->scratch3.release(); c->d_plan.release();
-  for (auto& e : c->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-  if (c->fork_ev) {
-    cudaEventDestroy(c->fork_ev);
-    for (int i = 0; i < trpa_ctx::kAux; ++i) { cudaStreamDestroy(c->aux[i]); cudaEventDestroy(c->aux_done[i]); }
-  }
-  if (c->h_counters) cudaFreeHost(c->h_counters);
-  if (c->own_stream) cudaStreamDestroy(c->stream);
+  c->d_pairs_sorted.release(); c->d_stage.release();
+  c->arena_planes.release(); c->arena_n.release(); c->arena_aa.release();
+  for (int i = trpa_ctx::kMaxPipes - 1; i >= 0; --i) c->pipe[i].release();
   delete c;
 }
 
@@ -465,6 +508,8 @@ int trpa_set_tuning(trpa_ctx* c, const char* key, int64_t value) {
   if (k == "band_k0") c->band_k0 = value < 0 ? 0u : (u32)std::min<int64_t>(value, 0xfffffe);
   else if (k == "plan_lanes") c->plan_lanes = value < 0 ? 0u : (u32)std::min<int64_t>(value, 1 << 30);
   else if (k == "myers_version") c->myers_version = value == 2 ? 2 : 3;
+  else if (k == "force_shape") c->force_shape = value < 0 || value >= kNumW * kNumL ? -1 : (int)value;
+  else if (k == "pipes") c->n_pipes = (int)std::max<int64_t>(1, std::min<int64_t>(trpa_ctx::kMaxPipes, value));
   else { set_error("unknown tuning key: " + k); return TRPA_ERR_ARG; }
   return 0;
 }
@@ -638,17 +683,29 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
   // extensions can add at most the query range; sequences are clipped to the store anyway
   max_len = std::min<u64>((u64)max_len + Q.max_len, std::max(R.max_len, Q.max_len));
   c->max_stage_len = max_len;
-  units_cap = std::min(units_cap, std::max<u64>(total_bound, 1));
-  if (max_bound > units_cap) { set_error("staging arena too small for the largest segment; raise trpa_set_arena_bytes"); return TRPA_ERR_NOMEM; }
+  // chunks of segments: every pipe works on one chunk at a time inside its own arena region
+  const int K = (c->n_pipes > 1 && n_segs >= 8192u) ? c->n_pipes : 1;
+  u64 cap_pipe = units_cap / K;
+  cap_pipe = std::min(cap_pipe, (total_bound + K - 1) / K + max_bound);
+  cap_pipe = std::max<u64>(cap_pipe, 1);
+  if (max_bound > cap_pipe) { set_error("staging arena too small for the largest segment; raise trpa_set_arena_bytes"); return TRPA_ERR_NOMEM; }
+  const u64 n_chunks_min = std::max<u64>(K, (total_bound + cap_pipe - 1) / cap_pipe);
+  const u64 target = std::min<u64>(cap_pipe, (total_bound + n_chunks_min - 1) / n_chunks_min + 1);
   c->chunk_begin.clear();
+  c->chunk_qoff.clear();
   c->chunk_begin.push_back(0);
-  u64 acc = 0;
+  c->chunk_qoff.push_back(0);
+  u64 acc = 0, qacc = 0;
   for (u32 s = 0; s < n_segs; ++s) {
-    if (acc + bound[s] > units_cap) { c->chunk_begin.push_back(s); acc = 0; }
+    if (acc && (acc + bound[s] > cap_pipe || acc >= target)) { c->chunk_begin.push_back(s); c->chunk_qoff.push_back(qacc); acc = 0; }
     acc += bound[s];
+    qacc += (u64)segs[s].cand_count + 1u;
   }
   c->chunk_begin.push_back(n_segs);
-  c->arena_units = units_cap;
+  c->chunk_qoff.push_back(qacc);
+  c->run_pipes = K;
+  c->arena_units = cap_pipe;      // per pipe
+  units_cap = cap_pipe * K;
 
   const size_t nslots = (size_t)n_cands + n_segs;
   if (c->d_segs.ensure(n_segs + 1) || c->d_cands.ensure(n_cands + 1) || c->d_results.ensure(n_segs + 1) ||
@@ -656,8 +713,7 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
       c->d_bf_d.ensure(nslots + 1) || c->d_bf_node.ensure(nslots + 1) || c->d_cflags.ensure(n_cands + 1) ||
       c->d_og_i.ensure(n_cands + 1) || c->d_tag.ensure(n_cands + 1) || c->d_og_d.ensure(n_cands + 1) || c->d_res.ensure(2 * nslots + 2) ||
       c->d_descs.ensure(nslots + 1) || c->d_pairs.ensure(nslots + 1) || c->d_pairs_sorted.ensure(nslots + 1) ||
-      c->d_stage.ensure(nslots + 1) || c->d_counters.ensure(kNumCounters) || c->d_hist.ensure(3 * kNumShapes) ||
-      c->d_buckets.ensure(kNumShapes))
+      c->d_stage.ensure(nslots + 1))
     return TRPA_ERR_NOMEM;
   if (protein) { if (c->arena_aa.ensure(units_cap + 16)) return TRPA_ERR_NOMEM; }
   else { if (c->arena_planes.ensure(units_cap + 2) || c->arena_n.ensure(units_cap + 2)) return TRPA_ERR_NOMEM; }
@@ -667,6 +723,127 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
   c->batch_ready = true;
   return 0;
 }
+
+namespace trpa {
+
+enum PipeState { PS_IDLE = 0, PS_WAIT_DECIDE, PS_WAIT_PLAN, PS_DONE };
+
+// decide kernel of the pipe's chunk + read-back of the round counters (asynchronous)
+static int enqueue_decide(trpa_ctx* c, Pipe& P) {
+  const int ev = begin_event(P, EV_DECIDE);
+  decide_kernel<<<(P.se - P.sb + 63) / 64, 64, 0, P.stream>>>(P.B, P.sb, P.se);
+  CK(cudaGetLastError());
+  end_event(P, ev);
+  c->prof.launches_decide++;
+  CK(cudaMemcpyAsync(P.h_counters, P.d_counters.p, sizeof(u32) * kNumCounters, cudaMemcpyDeviceToHost, P.stream));
+  P.state = PS_WAIT_DECIDE;
+  return 0;
+}
+
+// hand the next chunk of the batch to pipe P (or retire it)
+static int start_chunk(trpa_ctx* c, Pipe& P, int pipe_index, size_t& next_chunk, const Batch& base) {
+  while (next_chunk + 1 < c->chunk_begin.size() && c->chunk_begin[next_chunk] == c->chunk_begin[next_chunk + 1]) ++next_chunk;
+  if (next_chunk + 1 >= c->chunk_begin.size()) { P.state = PS_DONE; return 0; }
+  const size_t ch = next_chunk++;
+  P.sb = c->chunk_begin[ch]; P.se = c->chunk_begin[ch + 1];
+  P.B = base;
+  P.B.pairs = c->d_pairs.p + c->chunk_qoff[ch];
+  P.B.stage = c->d_stage.p + c->chunk_qoff[ch];
+  P.B.counters = P.d_counters.p;
+  P.B.arena_base = (u32)(c->arena_units * (u64)pipe_index);
+  P.B.arena_capacity = (u32)c->arena_units;
+  P.B.spec_k = 0;
+  P.pairs = P.B.pairs;
+  P.sorted = c->d_pairs_sorted.p + c->chunk_qoff[ch];
+  CK(cudaMemsetAsync(P.d_counters.p, 0, sizeof(u32) * kNumCounters, P.stream));
+  init_state_kernel<<<(P.se - P.sb + 255) / 256, 256, 0, P.stream>>>(c->d_state.p + P.sb, P.se - P.sb);
+  CK(cudaGetLastError());
+  return enqueue_decide(c, P);
+}
+
+// advance pipe P by one host step: wait for what it has in flight, then enqueue its next phase
+static int step_pipe(trpa_ctx* c, Pipe& P, int pipe_index, size_t& next_chunk, const Batch& base) {
+  const Store& Q = c->store[TRPA_STORE_QUERY];
+  const Store& R = c->store[TRPA_STORE_REF];
+  const bool protein = Q.alphabet == TRPA_ALPHA_AA;
+  const bool v3 = c->myers_version == 3;
+  CK(cudaStreamSynchronize(P.stream));
+  harvest_events(c, P);
+  if (P.state == PS_WAIT_DECIDE) {
+    const u32 n_pairs = P.h_counters[CN_PAIRS], n_stage = P.h_counters[CN_STAGE], n_active = P.h_counters[CN_ACTIVE];
+    // look-ahead budget of the NEXT decide round: only as much as the GPU has idle capacity for
+    // (about 16 resident warps per SM shared by the pipes, one pair per warp when pairs are scarce)
+    if (c->lookahead >= 0) P.B.spec_k = (u32)c->lookahead;
+    else {
+      const u32 cap = (u32)c->num_sms * 16u / (u32)c->run_pipes;
+      P.B.spec_k = n_active ? std::min<u32>(16u, cap / n_active > 0 ? cap / n_active - 1 : 0) : 0;
+    }
+    if (P.h_counters[CN_OVERFLOW]) { set_error("internal: staging arena overflow"); return TRPA_ERR_STATE; }
+    if (n_pairs == 0) {
+      if (n_active) { set_error("internal: segments active without pending alignments"); return TRPA_ERR_STATE; }
+      // algorithmic staging traffic of the chunk: packed store bits read + staged bits written
+      // (nt: 3 planes x 4 B per 32-base word each way; aa: 5 bit read + 1 byte written per residue)
+      const u64 units = P.h_counters[CN_ARENA];
+      c->prof.bytes_stage += protein ? (units * 13) / 8 : units * 24;
+      if (!protein && v3) { const int rc = harvest_band_stats(c, P); if (rc) return rc; }
+      return start_chunk(c, P, pipe_index, next_chunk, base);
+    }
+    P.n_pairs = n_pairs;
+    c->prof.rounds++;
+    c->prof.pairs += n_pairs;
+    // --- stage
+    int ev = begin_event(P, EV_STAGE);
+    if (protein)
+      CK(launch_stage_aa(P.B.stage, n_stage, Q.packed.p, Q.woff.p, R.packed.p, R.woff.p, c->d_descs.p, c->arena_aa.p, P.stream));
+    else
+      CK(launch_stage_nt(P.B.stage, n_stage, Q.planes.p, Q.nplane.p, Q.woff.p, R.planes.p, R.nplane.p, R.woff.p,
+                         c->d_descs.p, c->arena_planes.p, c->arena_n.p, P.stream));
+    end_event(P, ev);
+    if (n_stage) c->prof.launches_stage++;
+    if (protein) {
+      int2* scr = nullptr; u32 stride = 0;
+      if (c->max_stage_len > 512) {
+        stride = c->max_stage_len + 2;
+        if (P.scratch_aa.ensure((size_t)n_pairs * stride)) return TRPA_ERR_NOMEM;
+        scr = P.scratch_aa.p;
+      }
+      ev = begin_event(P, EV_PROTEIN);
+      CK(launch_protein(P.pairs, n_pairs, c->d_descs.p, c->arena_aa.p, (int2*)c->d_res.p, scr, stride,
+                        c->max_stage_len, P.stream));
+      end_event(P, ev);
+      c->prof.launches_protein++;
+      CK(cudaMemsetAsync(P.d_counters.p + CN_PAIRS, 0, sizeof(u32) * 3, P.stream));
+      return enqueue_decide(c, P);
+    }
+    // --- plan: threshold + shape of every pair, counting sort by shape, histogram to the host
+    ev = begin_event(P, EV_OTHER);
+    u32* h_hist = P.h_counters + kNumCounters;
+    const int rc = v3 ? bucket_pairs3(c, P, P.pairs, n_pairs, c->d_descs.p, c->arena_planes.p, c->arena_n.p, P.sorted, h_hist)
+                      : bucket_pairs(c, P, P.pairs, n_pairs, c->d_descs.p, P.sorted, h_hist);
+    if (rc) return rc;
+    end_event(P, ev);
+    c->prof.launches_other += v3 ? 3 : 3;
+    P.state = PS_WAIT_PLAN;
+    return 0;
+  }
+  if (P.state == PS_WAIT_PLAN) {
+    // --- align: one persistent launch per non-empty shape
+    const u32* h_hist = P.h_counters + kNumCounters;
+    const int ev = begin_event(P, EV_MYERS);
+    const int rc = v3 ? launch_myers_shapes3(c, P, h_hist, P.sorted, c->d_descs.p, c->arena_planes.p, c->arena_n.p,
+                                             c->d_res.p, c->max_stage_len)
+                      : launch_myers_shapes(c, P, h_hist, P.sorted, c->d_descs.p, c->arena_planes.p, c->arena_n.p,
+                                            c->d_res.p, c->max_stage_len);
+    if (rc) return rc;
+    end_event(P, ev);
+    // reset the per-round counters, keep the arena cursor
+    CK(cudaMemsetAsync(P.d_counters.p + CN_PAIRS, 0, sizeof(u32) * 3, P.stream));
+    return enqueue_decide(c, P);
+  }
+  return 0;
+}
+
+}  // namespace trpa
 
 int trpa_batch_run(trpa_ctx* c) {
   if (!c) { set_error("null ctx"); return TRPA_ERR_ARG; }
@@ -689,90 +866,42 @@ int trpa_batch_run(trpa_ctx* c) {
   B.tag = c->d_tag.p; B.spec_k = 0;
   B.og_i = c->d_og_i.p; B.og_d = c->d_og_d.p; B.bf_d = c->d_bf_d.p; B.bf_node = c->d_bf_node.p;
   B.res_nt = c->d_res.p; B.res_aa = c->d_res.p;
-  B.descs = c->d_descs.p; B.arena_capacity = (u32)c->arena_units;
-  B.pairs = c->d_pairs.p; B.stage = c->d_stage.p; B.counters = c->d_counters.p; B.results = c->d_results.p;
-
-  init_state_kernel<<<(n_segs + 255) / 256, 256, 0, c->stream>>>(c->d_state.p, n_segs);
-  CK(cudaGetLastError());
+  B.descs = c->d_descs.p; B.arena_capacity = (u32)c->arena_units; B.arena_base = 0;
+  B.pairs = c->d_pairs.p; B.stage = c->d_stage.p; B.counters = nullptr; B.results = c->d_results.p;
   if (protein) CK(ensure_blosum_constant(c->device));
 
-  for (size_t ch = 0; ch + 1 < c->chunk_begin.size(); ++ch) {
-    const u32 sb = c->chunk_begin[ch], se = c->chunk_begin[ch + 1];
-    if (se == sb) continue;
-    CK(cudaMemsetAsync(c->d_counters.p, 0, sizeof(u32) * kNumCounters, c->stream));
-    for (u32 round = 0;; ++round) {
-      int ev = begin_event(c, EV_DECIDE);
-      decide_kernel<<<(se - sb + 63) / 64, 64, 0, c->stream>>>(B, sb, se);
-      CK(cudaGetLastError());
-      end_event(c, ev);
-      c->prof.launches_decide++;
-      CK(cudaMemcpyAsync(c->h_counters, c->d_counters.p, sizeof(u32) * kNumCounters, cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      harvest_events(c);
-      const u32 n_pairs = c->h_counters[CN_PAIRS], n_stage = c->h_counters[CN_STAGE], n_active = c->h_counters[CN_ACTIVE];
-      // look-ahead budget of the NEXT decide round: only as much as the GPU has idle lanes for
-      // (about 16 resident warps per SM, one pair per warp when pairs are scarce)
-      if (c->lookahead >= 0) B.spec_k = (u32)c->lookahead;
-      else {
-        const u32 cap = (u32)c->num_sms * 16u;
-        B.spec_k = n_active ? std::min<u32>(16u, cap / n_active > 0 ? cap / n_active - 1 : 0) : 0;
+  // the chunks of the batch are worked on by run_pipes pipes at the same time; the host advances
+  // them round-robin, so while it waits for one pipe the others have work queued on the GPU
+  const int K = c->run_pipes;
+  for (int k = 0; k < K; ++k) { const int rc = c->pipe[k].init(nullptr); if (rc) return rc; }
+  if (K > 1) {   // the other pipes start after whatever is queued on the context's stream
+    Pipe& P0 = c->pipe[0];
+    if (!P0.fork_ev) {
+      CK(cudaEventCreateWithFlags(&P0.fork_ev, cudaEventDisableTiming));
+      for (int i = 0; i < Pipe::kAux; ++i) {
+        CK(cudaStreamCreateWithFlags(&P0.aux[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&P0.aux_done[i], cudaEventDisableTiming));
       }
-      if (c->h_counters[CN_OVERFLOW]) { set_error("internal: staging arena overflow"); return TRPA_ERR_STATE; }
-      if (n_pairs == 0) {
-        if (n_active) { set_error("internal: segments active without pending alignments"); return TRPA_ERR_STATE; }
-        // algorithmic staging traffic of the chunk: packed store bits read + staged bits written
-        // (nt: 3 planes x 4 B per 32-base word each way; aa: 5 bit read + 1 byte written per residue)
-        const u64 units = c->h_counters[CN_ARENA];
-        c->prof.bytes_stage += protein ? (units * 13) / 8 : units * 24;
-        if (!protein && c->myers_version == 3) { const int rc = harvest_band_stats(c); if (rc) return rc; }
-        break;
-      }
-      c->prof.rounds++;
-      c->prof.pairs += n_pairs;
-      // --- stage
-      ev = begin_event(c, EV_STAGE);
-      if (protein)
-        CK(launch_stage_aa(c->d_stage.p, n_stage, Q.packed.p, Q.woff.p, R.packed.p, R.woff.p, c->d_descs.p, c->arena_aa.p, c->stream));
-      else
-        CK(launch_stage_nt(c->d_stage.p, n_stage, Q.planes.p, Q.nplane.p, Q.woff.p, R.planes.p, R.nplane.p, R.woff.p,
-                           c->d_descs.p, c->arena_planes.p, c->arena_n.p, c->stream));
-      end_event(c, ev);
-      if (n_stage) c->prof.launches_stage++;
-      // --- align
-      if (protein) {
-        int2* scr = nullptr; u32 stride = 0;
-        if (c->max_stage_len > 512) {
-          stride = c->max_stage_len + 2;
-          if (c->scratch_aa.ensure((size_t)n_pairs * stride)) return TRPA_ERR_NOMEM;
-          scr = c->scratch_aa.p;
-        }
-        ev = begin_event(c, EV_PROTEIN);
-        CK(launch_protein(c->d_pairs.p, n_pairs, c->d_descs.p, c->arena_aa.p, (int2*)c->d_res.p, scr, stride,
-                          c->max_stage_len, c->stream));
-        end_event(c, ev);
-        c->prof.launches_protein++;
-      } else {
-        ev = begin_event(c, EV_OTHER);
-        u32* h_hist = c->h_counters + kNumCounters;
-        const bool v3 = c->myers_version == 3;
-        int rc = v3 ? bucket_pairs3(c, c->d_pairs.p, n_pairs, c->d_descs.p, c->arena_planes.p, c->arena_n.p, c->d_pairs_sorted.p, h_hist)
-                    : bucket_pairs(c, c->d_pairs.p, n_pairs, c->d_descs.p, c->d_pairs_sorted.p, h_hist);
-        if (rc) return rc;
-        end_event(c, ev);
-        c->prof.launches_other += v3 ? 4 : 3;
-        ev = begin_event(c, EV_MYERS);
-        rc = v3 ? launch_myers_shapes3(c, h_hist, c->d_pairs_sorted.p, c->d_descs.p, c->arena_planes.p, c->arena_n.p,
-                                       c->d_res.p, c->max_stage_len)
-                : launch_myers_shapes(c, h_hist, c->d_pairs_sorted.p, c->d_descs.p, c->arena_planes.p, c->arena_n.p,
-                                      c->d_res.p, c->max_stage_len);
-        if (rc) return rc;
-        end_event(c, ev);
-      }
-      // reset the per-round counters, keep the arena cursor
-      CK(cudaMemsetAsync(c->d_counters.p + CN_PAIRS, 0, sizeof(u32) * 3, c->stream));
     }
+    CK(cudaEventRecord(P0.fork_ev, P0.stream));
+    for (int k = 1; k < K; ++k) CK(cudaStreamWaitEvent(c->pipe[k].stream, P0.fork_ev, 0));
   }
-  // totals for the profile
+  size_t next_chunk = 0;
+  for (int k = 0; k < K; ++k) { const int rc = start_chunk(c, c->pipe[k], k, next_chunk, B); if (rc) return rc; }
+  for (;;) {
+    bool any = false;
+    for (int k = 0; k < K; ++k) {
+      Pipe& P = c->pipe[k];
+      if (P.state == PS_DONE) continue;
+      any = true;
+      const int rc = step_pipe(c, P, k, next_chunk, B);
+      if (rc) {
+        for (int q = 0; q < K; ++q) cudaStreamSynchronize(c->pipe[q].stream);
+        return rc;
+      }
+    }
+    if (!any) break;
+  }
   return 0;
 }
 
@@ -824,8 +953,7 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   DevBuf<SeqDesc> d_sd; DevBuf<uint2> planes; DevBuf<u32> nplane; DevBuf<PairDesc> d_pairs, d_sorted; DevBuf<int32_t> d_out;
   DevBuf<u32> d_cnt;
   if (d_sd.ensure(n_seq + 1) || planes.ensure(words + 2) || nplane.ensure(words + 2) || d_pairs.ensure(n_pairs) ||
-      d_sorted.ensure(n_pairs) || d_out.ensure(n_pairs) || d_cnt.ensure(kNumCounters) || c->d_hist.ensure(3 * kNumShapes) ||
-      c->d_buckets.ensure(kNumShapes))
+      d_sorted.ensure(n_pairs) || d_out.ensure(n_pairs) || d_cnt.ensure(kNumCounters))
     return TRPA_ERR_NOMEM;
   CK(cudaMemcpyAsync(d_sd.p, sd.data(), sizeof(SeqDesc) * n_seq, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemsetAsync(planes.p, 0, (words + 2) * sizeof(uint2), c->stream));
@@ -845,23 +973,25 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   CK(cudaMemcpyAsync(d_pairs.p, hp.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, c->stream));
   std::vector<u32> h_hist(kNumShapes, 0);
   const bool v3 = c->myers_version == 3;
-  rc = v3 ? bucket_pairs3(c, d_pairs.p, n_pairs, d_sd.p, planes.p, nplane.p, d_sorted.p, c->h_counters + kNumCounters)
-          : bucket_pairs(c, d_pairs.p, n_pairs, d_sd.p, d_sorted.p, c->h_counters + kNumCounters);
+  Pipe& P = c->pipe[0];
+  rc = v3 ? bucket_pairs3(c, P, d_pairs.p, n_pairs, d_sd.p, planes.p, nplane.p, d_sorted.p, P.h_counters + kNumCounters)
+          : bucket_pairs(c, P, d_pairs.p, n_pairs, d_sd.p, d_sorted.p, P.h_counters + kNumCounters);
   if (rc) return rc;
-  memcpy(h_hist.data(), c->h_counters + kNumCounters, sizeof(u32) * kNumShapes);
+  CK(cudaStreamSynchronize(P.stream));
+  memcpy(h_hist.data(), P.h_counters + kNumCounters, sizeof(u32) * kNumShapes);
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   if (repeat < 1) repeat = 1;
   // one untimed pass when timing is requested
   if (kernel_ms && repeat > 1) {
-    rc = v3 ? launch_myers_shapes3(c, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len)
-            : launch_myers_shapes(c, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
+    rc = v3 ? launch_myers_shapes3(c, P, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len)
+            : launch_myers_shapes(c, P, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
     if (rc) return rc;
   }
   CK(cudaEventRecord(e0, c->stream));
   for (int r = 0; r < repeat; ++r) {
-    rc = v3 ? launch_myers_shapes3(c, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len)
-            : launch_myers_shapes(c, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
+    rc = v3 ? launch_myers_shapes3(c, P, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len)
+            : launch_myers_shapes(c, P, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
     if (rc) return rc;
   }
   CK(cudaEventRecord(e1, c->stream));
@@ -871,7 +1001,7 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   CK(cudaEventElapsedTime(&ms, e0, e1));
   if (kernel_ms) *kernel_ms = ms / repeat;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  if (v3) { rc = harvest_band_stats(c); if (rc) return rc; }
+  if (v3) { rc = harvest_band_stats(c, P); if (rc) return rc; }
   d_chars.release(); d_off.release(); d_sd.release(); planes.release(); nplane.release(); d_pairs.release();
   d_sorted.release(); d_out.release(); d_cnt.release(); d_flags.release();
   return 0;
@@ -904,8 +1034,8 @@ int trpa_protein_align_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   int2* scr = nullptr; u32 stride = 0;
   if (max_len > 512) {
     stride = max_len + 2;
-    if (c->scratch_aa.ensure((size_t)n_pairs * stride)) return TRPA_ERR_NOMEM;
-    scr = c->scratch_aa.p;
+    if (c->pipe[0].scratch_aa.ensure((size_t)n_pairs * stride)) return TRPA_ERR_NOMEM;
+    scr = c->pipe[0].scratch_aa.p;
   }
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));

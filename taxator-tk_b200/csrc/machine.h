@@ -102,7 +102,8 @@ struct Batch {
   const int32_t* res_aa;     // int2 {mutual, #diag}
   // staged sequence table: [s] query segment of s; [n_segs + c] candidate c
   SeqDesc* descs;
-  uint32_t arena_capacity;   // words (NT) / bytes (AA)
+  uint32_t arena_base;       // first unit of this pipeline's arena region
+  uint32_t arena_capacity;   // units of the region: words (NT) / bytes (AA)
   // queues
   PairDesc* pairs;
   StageReq* stage;
@@ -153,7 +154,7 @@ struct Machine {
     const uint32_t units = B.protein ? ((len + 3u) & ~3u) : ((len + 31u) >> 5);
     const uint32_t woff = TRPA_ATOMIC_ADD_U32(&B.counters[CN_ARENA], units);
     if ((uint64_t)woff + units > B.arena_capacity) { TRPA_ATOMIC_ADD_U32(&B.counters[CN_OVERFLOW], 1u); }
-    B.descs[desc] = SeqDesc{woff, len, 0u, 0u};
+    B.descs[desc] = SeqDesc{B.arena_base + woff, len, 0u, 0u};
     const uint32_t q = TRPA_ATOMIC_ADD_U32(&B.counters[CN_STAGE], 1u);
     B.stage[q] = StageReq{desc, store, seq, (uint32_t)b, rev};
   }

@@ -93,7 +93,7 @@ cudaError_t launch_myers(int shape, const PairDesc* pairs, u32 count, const SeqD
 // when pairs are plentiful, latency when they are scarce).  pad <- shape | k0 << 8; histogram.
 __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const SeqDesc* __restrict__ descs,
                             const uint2* __restrict__ planes, const u32* __restrict__ nplane,
-                            u32* __restrict__ hist, u32 lanes_total, int band) {
+                            u32* __restrict__ hist, u32 lanes_total, int band, int force_shape) {
   const u32 lane = threadIdx.x & 31;
   const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -140,6 +140,7 @@ __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const Seq
       const int ob = __shfl_xor_sync(0xffffffffu, best, o);
       if (ok < key || (ok == key && ob < best)) { key = ok; best = ob; }
     }
+    if (force_shape >= 0) best = force_shape;
     if (lane == 0) {
       const int shape = shape_id(best % kNumW, best / kNumW, hasn);
       pairs[p].pad = (k0 << 8) | (u32)shape;
@@ -149,10 +150,10 @@ __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const Seq
 }
 
 cudaError_t launch_plan(PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, const uint2* planes, const u32* nplane,
-                        u32* hist, u32 lanes_total, int band, cudaStream_t stream) {
+                        u32* hist, u32 lanes_total, int band, int force_shape, cudaStream_t stream) {
   if (n_pairs == 0) return cudaSuccess;
   const u32 blocks = std::min<u32>((n_pairs + 3) / 4, 148u * 16u);
-  plan_kernel<<<blocks, 128, 0, stream>>>(pairs, n_pairs, descs, planes, nplane, hist, lanes_total, band);
+  plan_kernel<<<blocks, 128, 0, stream>>>(pairs, n_pairs, descs, planes, nplane, hist, lanes_total, band, force_shape);
   return cudaGetLastError();
 }
 

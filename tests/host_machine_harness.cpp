@@ -52,7 +52,7 @@ extern "C" int hm_predict_batch(
   B.tag = tag.data(); B.spec_k = spec_k;
   B.og_i = og_i.data(); B.og_d = og_d.data(); B.bf_d = bf_d.data(); B.bf_node = bf_node.data();
   B.res_nt = res_nt.data(); B.res_aa = res_aa.data();
-  B.descs = descs.data(); B.arena_capacity = 0xffffffffu;
+  B.descs = descs.data(); B.arena_capacity = 0xffffffffu; B.arena_base = 0;
   B.pairs = pairs.data(); B.stage = stage.data(); B.counters = counters.data(); B.results = results;
 
   uint32_t rounds = 0;

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the RPA hot path (BASELINE.json metric: query segments/s and GCUPS).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c5|tiny] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4|c5|tiny] [--impl ours|reference]
 
 One "step" = one pass of the whole batched RPA path (decide / stage / align rounds until every
 segment is placed) over one batch of synthetic query segments.  Default workload = BASELINE.json
@@ -48,6 +48,10 @@ WORKLOADS = {
     "c3": dict(desc="protein RPA (BLOSUM62, linear gap), 50k 300-aa segments", protein=True,
                cfg=dict(n_genomes=400, genome_len=400, n_queries=50000, query_len=(300, 300), n_cand=30,
                         levels=(4, 8, 16, 40, 100)), cpu_sample=600),
+    # configs[3]: the per-GPU shard (1/8) of the 2M-segment batch, mixed 0.5-20 kb, length-bucketed on the device
+    "c4": dict(desc="nucleotide RPA, 250k segments per GPU (1/8 of 2M), mixed 0.5-20 kb, ~30 candidate refs", protein=False,
+               cfg=dict(n_genomes=400, genome_len=100000, n_queries=250000, query_len=(500, 20000), n_cand=30,
+                        levels=(4, 8, 16, 40, 100)), cpu_sample=100),
     # configs[4], scaled to one GPU-minute per step
     "c5": dict(desc="long-read nucleotide RPA, 10-50 kb noisy reads (15% error)", protein=False,
                cfg=dict(n_genomes=100, genome_len=200000, n_queries=4000, query_len=(10000, 50000), n_cand=20,
@@ -201,6 +205,8 @@ def main():
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--segments", type=int, default=None, help="override segments per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lookahead", type=int, default=-1, help="look-ahead budget (-1: automatic)")
+    ap.add_argument("--tune", action="append", default=[], help="key=value tuning hook (trpa_set_tuning)")
     ap.add_argument("--band", type=int, default=1, help="1: exact Ukkonen band (default), 0: full DP matrices (A/B)")
     args = ap.parse_args()
 
@@ -242,6 +248,10 @@ def main():
     t_load = time.time() - t0
     alu_peak = ctx.int_alu_peak()
     ctx.set_band(args.band)
+    ctx.set_lookahead(args.lookahead)
+    for kv in args.tune:
+        k, v = kv.split("=")
+        ctx.set_tuning(k, int(v))
 
     # pinned host buffers for the e2e path
     segs_t = torch.from_numpy(fd.segs.view(np.uint8).copy()).pin_memory()

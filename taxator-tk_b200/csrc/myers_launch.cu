@@ -129,10 +129,15 @@ __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const Seq
     const BandGeom g = band_from_k(m ? m : 1u, n ? n : 1u, k0 >= kPadKFull ? 0xffffffffu : k0, !band);
     uint64_t key = ~0ull;
     int best = 0;
-    for (int id = (int)lane; id < kNumW * kNumL; id += 32) {
-      const ShapeCost sc = band_shape_cost(g, id % kNumW, id / kNumW);
-      const uint64_t kk = sc.cost * n_pairs + sc.time * lanes_total;
-      if (kk < key) { key = kk; best = id; }
+    // 32 candidates, one per lane: W in {2, 4, 8, 12, 16} x L in {1 .. 32}, + W in {20, 24} at L = 32
+    // (long patterns with wide bands); W = 1 never wins (per-column overhead)
+    {
+      int w, l;
+      if (lane < 30) { w = 1 + (int)(lane % 5u); l = (int)(lane / 5u); }
+      else { w = 6 + (int)(lane - 30u); l = kNumL - 1; }
+      const ShapeCost sc = band_shape_cost(g, w, l);
+      key = sc.cost * n_pairs + sc.time * lanes_total;
+      best = l * kNumW + w;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -97,20 +97,29 @@ TRPA_HD BandGeom band_from_k(uint32_t m, uint32_t n, uint32_t k, bool force_full
   return g;
 }
 
-// Group steps the rotating schedule needs for one attempt (gap evaluated at both ends of a round).
+// Group steps the rotating schedule needs for one attempt (gap evaluated at both ends of a round;
+// long schedules are sampled: the gap is piecewise linear in the round index).
 TRPA_HD uint64_t band_steps(const BandGeom& g, int W, int L) {
   const uint32_t R = 32u * (uint32_t)W;
   const uint32_t mwords = (g.m + 31u) >> 5, nblk = (g.n + 31u) >> 5;
   const uint32_t S = (mwords + W - 1) / W;
   uint64_t off = 0;
-  for (uint32_t s0 = 0; s0 + L < S; s0 += L) {
-    int gap = 1;
-    const uint32_t l_hi = (S - L - 1u - s0) < (uint32_t)(L - 1) ? (S - L - 1u - s0) : (uint32_t)(L - 1);
-    const int t0 = (int)g.b1(s0, R) - (int)g.b0(s0 + L, R) + 1 - L;
-    const int t1 = (int)g.b1(s0 + l_hi, R) - (int)g.b0(s0 + l_hi + L, R) + 1 - L;
-    if (t0 > gap) gap = t0;
-    if (t1 > gap) gap = t1;
-    off += (uint64_t)L + (uint64_t)gap;
+  if (S > (uint32_t)L) {
+    const uint32_t rounds = (S - 1u) / (uint32_t)L;          // rounds that have a successor round
+    const uint32_t stride = rounds > 12u ? (rounds + 11u) / 12u : 1u;
+    uint64_t acc = 0;
+    uint32_t n = 0;
+    for (uint32_t r = 0; r < rounds; r += stride, ++n) {
+      const uint32_t s0 = r * (uint32_t)L;
+      int gap = 1;
+      const uint32_t l_hi = (S - L - 1u - s0) < (uint32_t)(L - 1) ? (S - L - 1u - s0) : (uint32_t)(L - 1);
+      const int t0 = (int)g.b1(s0, R) - (int)g.b0(s0 + L, R) + 1 - L;
+      const int t1 = (int)g.b1(s0 + l_hi, R) - (int)g.b0(s0 + l_hi + L, R) + 1 - L;
+      if (t0 > gap) gap = t0;
+      if (t1 > gap) gap = t1;
+      acc += (uint64_t)L + (uint64_t)gap;
+    }
+    off = acc * rounds / n;
   }
   return off + ((S - 1u) % (uint32_t)L) + nblk;
 }

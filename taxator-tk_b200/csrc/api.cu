@@ -130,8 +130,6 @@ struct trpa_ctx {
   u32 n_nodes = 0, root = 0;
   Store store[2];
   // batch (whole batch resident)
-  std::vector<trpa_segment> h_segs;
-  std::vector<trpa_candidate> h_cands;
   std::vector<u32> chunk_begin;  // segment index boundaries
   std::vector<u64> chunk_qoff;   // start of the chunk's slice of the pair / stage queues
   int run_pipes = 1;             // pipes the uploaded batch was planned for
@@ -139,7 +137,8 @@ struct trpa_ctx {
   u32 max_stage_len = 0;
   bool batch_ready = false;
   DevBuf<trpa_segment> d_segs;
-  DevBuf<trpa_candidate> d_cands;
+  DevBuf<trpa_candidate> d_cands;      // SortFilter order
+  DevBuf<trpa_candidate> d_cands_raw;  // as uploaded
   DevBuf<trpa_result> d_results;
   DevBuf<SegState> d_state;
   DevBuf<float> d_qd, d_qsim, d_bf_d;
@@ -215,6 +214,31 @@ __global__ void scatter_kernel(const PairDesc* pairs, u32 n, u32* hist, PairDesc
     const PairDesc p = pairs[k];
     const u32 pos = atomicAdd(&hist[kNumShapes + (p.pad & 0xffu)], 1u);   // pad: shape | k0 << 8
     sorted[pos] = p;
+  }
+}
+
+// SortFilter on the device (core/src/alignmentsfilter.hh:171-190: stable sort, descending (score,
+// identities)): one warp per segment ranks every record against all others of its segment; the
+// original position breaks ties, which is exactly what a stable sort does.  raw -> sorted table.
+__global__ void sort_cands_kernel(const trpa_segment* __restrict__ segs, u32 n_segs,
+                                  const trpa_candidate* __restrict__ raw, trpa_candidate* __restrict__ out) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 s = warp; s < n_segs; s += nwarps) {
+    const trpa_segment sg = segs[s];
+    const trpa_candidate* in = raw + sg.cand_begin;
+    for (u32 i = lane; i < sg.cand_count; i += 32) {
+      const trpa_candidate x = in[i];
+      u32 rank = 0;
+      for (u32 j = 0; j < sg.cand_count; ++j) {
+        const float sj = in[j].score;
+        const u32 ij = in[j].identities;
+        const bool before = sj > x.score || (sj == x.score && (ij > x.identities || (ij == x.identities && j < i)));
+        rank += before ? 1u : 0u;
+      }
+      out[sg.cand_begin + rank] = x;
+    }
   }
 }
 
@@ -475,7 +499,7 @@ void trpa_destroy(trpa_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->t_parent.release(); c->t_left.release(); c->t_right.release(); c->t_depth.release();
   c->store[0].release(); c->store[1].release();
-  c->d_segs.release(); c->d_cands.release(); c->d_results.release(); c->d_state.release();
+  c->d_segs.release(); c->d_cands.release(); c->d_cands_raw.release(); c->d_results.release(); c->d_state.release();
   c->d_qd.release(); c->d_qsim.release(); c->d_bf_d.release(); c->d_cflags.release(); c->d_og_i.release(); c->d_tag.release();
   c->d_bf_node.release(); c->d_og_d.release(); c->d_res.release(); c->d_descs.release(); c->d_pairs.release();
   c->d_pairs_sorted.release(); c->d_stage.release();
@@ -601,62 +625,64 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
   if (Q.alphabet < 0 || R.alphabet < 0 || Q.alphabet != R.alphabet) { set_error("query/reference stores not loaded or of different alphabets"); return TRPA_ERR_STATE; }
   if ((u64)n_segs + n_cands >= 0xfffffff0ull) { set_error("batch too large"); return TRPA_ERR_ARG; }
   const bool protein = Q.alphabet == TRPA_ALPHA_AA;
-  // validate (the reference throws SequenceNotFound / TaxonNotFound at parse time)
+  // validate the segment table (the reference throws SequenceNotFound / TaxonNotFound at parse time)
   for (u32 s = 0; s < n_segs; ++s) {
     if ((u64)segs[s].cand_begin + segs[s].cand_count > n_cands) { set_error("segment candidate range out of bounds"); return TRPA_ERR_ARG; }
     if (segs[s].cand_count && segs[s].query_seq >= Q.n_seq) { set_error("segment query ordinal out of range"); return TRPA_ERR_ARG; }
   }
-  {
-    std::vector<int> bad(17, 0);
-    const u32 nseq = R.n_seq, nnodes = c->n_nodes;
-    parallel_blocks(n_cands, [&](size_t b, size_t e) {
-      int code = 0;
-      for (size_t k = b; k < e && !code; ++k) {
-        if (cands[k].ref_seq >= nseq) code = 1;
-        else if (cands[k].node >= nnodes) code = 2;
-        else if (cands[k].qstart > cands[k].qstop || cands[k].qstart == 0) code = 3;
-        else if (cands[k].rstart == 0 || cands[k].rstop == 0) code = 4;
-      }
-      if (code) bad[code] = 1;
-    });
-    if (bad[1]) { set_error("candidate reference ordinal out of range"); return TRPA_ERR_ARG; }
-    if (bad[2]) { set_error("candidate taxon node out of range"); return TRPA_ERR_ARG; }
-    if (bad[3]) { set_error("candidate query range invalid (qstart must be >= 1 and <= qstop)"); return TRPA_ERR_ARG; }
-    if (bad[4]) { set_error("candidate reference coordinates are 1-based"); return TRPA_ERR_ARG; }
+  // The raw tables go to the device straight from the caller's buffers (a DMA when they are pinned)
+  // while the host makes its one validation pass over them; SortFilter then runs on the device.
+  if (c->d_segs.ensure(n_segs + 1) || c->d_cands.ensure(n_cands + 1) || c->d_cands_raw.ensure(n_cands + 1)) return TRPA_ERR_NOMEM;
+  CK(cudaMemcpyAsync(c->d_segs.p, segs, sizeof(trpa_segment) * n_segs, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_cands_raw.p, cands, sizeof(trpa_candidate) * n_cands, cudaMemcpyHostToDevice, c->stream));
+  if (n_segs) {
+    const u32 blocks = std::min<u32>((n_segs + 7) / 8, (u32)c->num_sms * 8u);
+    sort_cands_kernel<<<blocks, 256, 0, c->stream>>>(c->d_segs.p, n_segs, c->d_cands_raw.p, c->d_cands.p);
   }
-  // A segment whose best score is below (1-t)*best (i.e. negative) realigns nothing in pass 0 and
-  // trips assert(!qgroup.empty()) in the reference (hh:563); reject it instead of guessing.
-  c->h_segs.assign(segs, segs + n_segs);
-  c->h_cands.resize(n_cands);
   std::vector<u64> bound(n_segs);
   std::vector<u32> maxspan(n_segs, 0);
   {
+    // A segment whose best score is negative (or NaN) realigns nothing in pass 0 and trips
+    // assert(!qgroup.empty()) in the reference (hh:563); reject it instead of guessing.
     const float factor = 1. - c->toppercent;
-    int neg = 0;
-    trpa_candidate* hc = c->h_cands.data();
-    const trpa_segment* hs = c->h_segs.data();
+    const u32 nseq = R.n_seq, nnodes = c->n_nodes;
+    int bad[6] = {0, 0, 0, 0, 0, 0};
     parallel_blocks(n_segs, [&](size_t b, size_t e) {
-      for (size_t s = b; s < e; ++s) {
-        const trpa_segment sg = hs[s];
-        trpa_candidate* dst = hc + sg.cand_begin;
-        std::copy(cands + sg.cand_begin, cands + sg.cand_begin + sg.cand_count, dst);
-        if (sg.cand_count >= 2) {
-          float best = dst[0].score;
-          for (u32 k = 1; k < sg.cand_count; ++k) best = std::max(best, dst[k].score);
-          if (!(best >= factor * best)) neg = 1;
-        }
-        sort_candidates(&sg, 1, hc);
-        bound[s] = segment_arena_bound(sg, hc, protein);
+      int code = 0;
+      for (size_t s = b; s < e && !code; ++s) {
+        const trpa_segment sg = segs[s];
+        const trpa_candidate* rc = cands + sg.cand_begin;
         u32 ms = 0;
+        float best = sg.cand_count ? rc[0].score : 0.f;
         for (u32 k = 0; k < sg.cand_count; ++k) {
-          const trpa_candidate& x = dst[k];
+          const trpa_candidate& x = rc[k];
+          if (x.ref_seq >= nseq) code = 1;
+          else if (x.node >= nnodes) code = 2;
+          else if (x.qstart > x.qstop || x.qstart == 0) code = 3;
+          else if (x.rstart == 0 || x.rstop == 0) code = 4;
+          if (code) break;
+          best = std::max(best, x.score);
           const u64 span = (x.rstart <= x.rstop ? (u64)x.rstop - x.rstart : (u64)x.rstart - x.rstop) + 1;
           ms = (u32)std::min<u64>(0xffffffffull, std::max<u64>(ms, span));
         }
+        if (code) break;
+        if (sg.cand_count >= 2 && !(best >= factor * best)) { code = 5; break; }
         maxspan[s] = ms;
+        bound[s] = segment_arena_bound(sg, cands, protein);
       }
+      if (code) bad[code] = 1;
     });
-    if (neg) { set_error("segment with negative best alignment score: undefined in the reference (hh:563)"); return TRPA_ERR_ARG; }
+    const char* msg = bad[1] ? "candidate reference ordinal out of range"
+                    : bad[2] ? "candidate taxon node out of range"
+                    : bad[3] ? "candidate query range invalid (qstart must be >= 1 and <= qstop)"
+                    : bad[4] ? "candidate reference coordinates are 1-based"
+                    : bad[5] ? "segment with negative best alignment score: undefined in the reference (hh:563)" : nullptr;
+    if (msg) {
+      cudaStreamSynchronize(c->stream);   // the copies read the caller's buffers
+      cudaGetLastError();
+      set_error(msg);
+      return TRPA_ERR_ARG;
+    }
   }
   c->n_segs = n_segs; c->n_cands = n_cands;
 
@@ -712,7 +738,7 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
   units_cap = cap_pipe * K;
 
   const size_t nslots = (size_t)n_cands + n_segs;
-  if (c->d_segs.ensure(n_segs + 1) || c->d_cands.ensure(n_cands + 1) || c->d_results.ensure(n_segs + 1) ||
+  if (c->d_results.ensure(n_segs + 1) ||
       c->d_state.ensure(n_segs + 1) || c->d_qd.ensure(n_cands + 1) || c->d_qsim.ensure(n_cands + 1) ||
       c->d_bf_d.ensure(nslots + 1) || c->d_bf_node.ensure(nslots + 1) || c->d_cflags.ensure(n_cands + 1) ||
       c->d_og_i.ensure(n_cands + 1) || c->d_tag.ensure(n_cands + 1) || c->d_og_d.ensure(n_cands + 1) || c->d_res.ensure(2 * nslots + 2) ||
@@ -721,8 +747,7 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
     return TRPA_ERR_NOMEM;
   if (protein) { if (c->arena_aa.ensure(units_cap + 16)) return TRPA_ERR_NOMEM; }
   else { if (c->arena_planes.ensure(units_cap + 2) || c->arena_n.ensure(units_cap + 2)) return TRPA_ERR_NOMEM; }
-  CK(cudaMemcpyAsync(c->d_segs.p, c->h_segs.data(), sizeof(trpa_segment) * n_segs, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_cands.p, c->h_cands.data(), sizeof(trpa_candidate) * n_cands, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   c->batch_ready = true;
   return 0;

@@ -66,3 +66,14 @@ def many_candidates():
     cfg = synth.SynthConfig(seed=25, n_genomes=300, genome_len=1500, n_queries=6, query_len=(400, 600), n_cand=300,
                             levels=(3, 6, 12, 30, 80))
     return ol.FlatData(synth.generate(cfg))
+
+
+def score_ties():
+    """Many equal (score, identities) keys: SortFilter is a STABLE sort (alignmentsfilter.hh:171-190),
+    so record order decides -- the device-side rank sort must reproduce it."""
+    fd = base(seed=26, n_queries=120)
+    c = fd.cands
+    c["score"] = (np.floor(c["score"] / 60.0) * 60.0).astype(np.float32)
+    c["identities"] = (c["identities"] // 16) * 16
+    c["identities"] = np.minimum(c["identities"], c["alnlen"] - 1).astype(np.uint32)
+    return fd

@@ -53,3 +53,8 @@ def test_parameters_x_and_t(ctx):
 def test_many_candidates_one_segment(ctx):
     """One segment with hundreds of records next to tiny ones (insertion sorts, long loops)."""
     check(ctx, edge_data.many_candidates())
+
+
+def test_stable_sort_with_ties(ctx):
+    """SortFilter runs on the device (rank sort with the record position as tie-break)."""
+    check(ctx, edge_data.score_ties())

@@ -35,3 +35,7 @@ def test_parameters_x_and_t():
 
 def test_many_candidates_one_segment():
     check(edge_data.many_candidates())
+
+
+def test_stable_sort_with_ties():
+    check(edge_data.score_ties())

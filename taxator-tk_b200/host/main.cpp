@@ -8,8 +8,10 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <thread>
 
 #include "driver.h"
+#include "ingest.h"
 #include "records.h"
 #include "rpa_model.h"
 #include "seqstore.h"
@@ -27,6 +29,8 @@ struct Options {
   float filterout = 0.5f, toppercent = 0.05f;
   std::vector<int> gpus = {0};
   size_t batch_segments = 200000;
+  size_t batch_bytes = 128u << 20;
+  bool legacy_ingest = false;
   bool timing = false;
 };
 
@@ -50,7 +54,9 @@ static void usage(std::ostream& os) {
         "  -x [ --heuristic-cutoff ] arg (=0.5)\n"
         "  -t [ --toppercent ] arg (=0.05)\n"
         "  --gpus arg (=0)                   comma separated CUDA device indices to shard segments over\n"
-        "  --batch-segments arg (=200000)    record sets per GPU batch\n"
+        "  --batch-segments arg (=200000)    record sets per GPU batch (record-at-a-time ingest)\n"
+        "  --batch-bytes arg (=134217728)    alignment text per GPU batch (fast ingest)\n"
+        "  --legacy-ingest                   parse records one at a time like the reference (always used with -o 1)\n"
         "  --timing                          print load/predict timing to stderr\n";
 }
 
@@ -66,7 +72,7 @@ static int parse_args(int argc, char** argv, Options& o) {
     {"query-sequences", 'q'}, {"query-sequences-index", 'v'}, {"ref-sequences", 'f'}, {"ref-sequences-index", 'i'},
     {"processors", 'p'}, {"logfile", 'l'}, {"dataformat", 'b'}, {"ranks", 'r'}, {"split-alignments", 's'},
     {"alignments-sorted", 'o'}, {"delete-notranks", 'd'}, {"heuristic-cutoff", 'x'}, {"toppercent", 't'},
-    {"gpus", 'G'}, {"batch-segments", 'B'}, {"timing", 'T'},
+    {"gpus", 'G'}, {"batch-segments", 'B'}, {"timing", 'T'}, {"batch-bytes", 'Y'}, {"legacy-ingest", 'L'},
     // accepted and ignored (other models' knobs)
     {"max-evalue", 'e'}, {"min-support", 'c'}, {"minscore", 'm'}, {"nbest", 'n'}, {"db-whitelist", 'w'},
     {"ignore-unclassified", 'u'}, {"citation", 'C'}, {"advanced-options", 'A'}};
@@ -80,7 +86,7 @@ static int parse_args(int argc, char** argv, Options& o) {
       if (eq != std::string::npos) { val = name.substr(eq + 1); has_val = true; name.resize(eq); }
       for (const auto& s : specs) if (name == s.lng) key = s.shrt;
     } else if (a.size() >= 2 && a[0] == '-') {
-      for (const auto& s : specs) if (a[1] == s.shrt && s.shrt != 'G' && s.shrt != 'B' && s.shrt != 'T' && s.shrt != 'C' && s.shrt != 'A') key = s.shrt;
+      for (const auto& s : specs) if (a[1] == s.shrt && s.shrt != 'G' && s.shrt != 'B' && s.shrt != 'T' && s.shrt != 'C' && s.shrt != 'A' && s.shrt != 'Y' && s.shrt != 'L') key = s.shrt;
       if (a.size() > 2) { val = a.substr(2); has_val = true; }
     }
     if (!key) throw TaxatorError("unrecognised option '" + a + "'");
@@ -119,6 +125,8 @@ static int parse_args(int argc, char** argv, Options& o) {
         break;
       }
       case 'B': o.batch_segments = std::stoul(need()); break;
+      case 'Y': o.batch_bytes = std::stoul(need()); break;
+      case 'L': o.legacy_ingest = true; break;
       case 'T': o.timing = true; break;
       case 'u': break;
       default: need(); break;  // ignored options with a value
@@ -147,9 +155,17 @@ int main(int argc, char** argv) {
     }
     const bool protein = opt.dataformat == "protein";
     auto t0 = std::chrono::steady_clock::now();
+    // CUDA context creation (about a second) overlaps the loading of the input files
+    std::thread warm([&opt]() {
+      for (int dev : opt.gpus) { trpa_ctx* c = trpa_create(dev, nullptr); if (c) trpa_destroy(c); }
+    });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } warm_joiner{warm};
     FlatTaxonomy tax = load_taxonomy_from_environment(opt.ranks, opt.delete_unmarked);
     SeqIdMapping mapping = load_mapping(opt.mapping);
     std::ofstream logsink(opt.logfile.c_str(), std::ios_base::app);
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    auto ta = std::chrono::steady_clock::now();
+    const double load_tax_s = secs(t0, ta);
 
     SeqStore q_store;
     if (opt.query_index.empty()) {
@@ -160,19 +176,41 @@ int main(int argc, char** argv) {
     // the reference store always uses index semantics (ids = first word / .fai name column); the
     // reference's in-memory mode returns un-reversed whole sequences for reverse hits
     // (sequencestorage.hh:122-130) and is not reproduced.
+    auto tb = std::chrono::steady_clock::now();
+    const double load_q_s = secs(ta, tb);
     SeqStore db_store = load_fasta_indexed(opt.ref, opt.ref_index.empty() ? opt.ref + ".fai" : opt.ref_index);
+    auto tc = std::chrono::steady_clock::now();
+    const double load_r_s = secs(tb, tc);
 
+    warm.join();
     RPAPredictionModelGPU model(&tax, q_store, db_store, opt.filterout, opt.toppercent, protein, opt.gpus);
     auto t1 = std::chrono::steady_clock::now();
+    const double load_gpu_s = secs(tc, t1);
 
     std::ios::sync_with_stdio(false);
-    RecordSetReader reader(std::cin, mapping, tax, opt.split_alignments, opt.alignments_sorted);
-    const uint64_t total_sets = run_prediction_stream(
-        reader, tax, opt.batch_segments,
-        [&](std::vector<RecordSet>& sets, std::vector<PredictionRecord>& precs, std::ostream& log) {
-          model.predictBatch(sets, precs, log);
-        },
-        std::cout, logsink);
+    uint64_t total_sets = 0;
+    StageTimes stage_times;
+    if (opt.legacy_ingest || opt.alignments_sorted) {
+      RecordSetReader reader(std::cin, mapping, tax, opt.split_alignments, opt.alignments_sorted);
+      total_sets = run_prediction_stream(
+          reader, tax, opt.batch_segments,
+          [&](std::vector<RecordSet>& sets, std::vector<PredictionRecord>& precs, std::ostream& log) {
+            model.predictBatch(sets, precs, log);
+          },
+          std::cout, logsink);
+    } else {
+      // parallel block parser -> flat tables -> GPU -> parallel GFF3 formatter, the stages overlapped
+      IngestOptions io;
+      io.split = opt.split_alignments;
+      io.block_bytes = opt.batch_bytes;
+      const bool want_log = opt.logfile != "/dev/null";
+      total_sets = run_prediction_fast(
+          stdin, mapping, tax, q_store, db_store, io,
+          [&](const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands, uint32_t n_cands, trpa_result* res) {
+            model.predictFlat(segs, n_segs, cands, n_cands, res);
+          },
+          std::cout, want_log ? &logsink : nullptr, &model.mutable_stats(), &stage_times);
+    }
     auto t2 = std::chrono::steady_clock::now();
     if (opt.timing) {
       auto st = model.stats();
@@ -181,6 +219,11 @@ int main(int argc, char** argv) {
       std::cerr << "taxator-b200: load " << load_s << " s, predict " << run_s << " s, " << total_sets << " segments, "
                 << st.alignments << " alignments, " << st.cells << " cells, " << (run_s > 0 ? st.cells / run_s / 1e9 : 0)
                 << " GCUPS" << std::endl;
+      if (stage_times.blocks)
+        std::cerr << "taxator-b200: stages busy: ingest " << stage_times.ingest_s << " s, gpu " << stage_times.predict_s
+                  << " s, output " << stage_times.output_s << " s over " << stage_times.blocks << " blocks" << std::endl;
+      std::cerr << "taxator-b200: load: taxonomy+mapping " << load_tax_s << " s, query store " << load_q_s << " s, reference store "
+                << load_r_s << " s, GPU set-up " << load_gpu_s << " s" << std::endl;
     }
     return EXIT_SUCCESS;
   } catch (std::exception& e) {

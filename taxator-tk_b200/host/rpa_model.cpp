@@ -121,19 +121,16 @@ void apply_results(const FlatTaxonomy& tax, const std::vector<trpa_segment>& seg
   }
 }
 
-void RPAPredictionModelGPU::predictBatch(std::vector<RecordSet>& recordsets, std::vector<PredictionRecord>& precs,
-                                         std::ostream& logsink) {
-  const size_t n = recordsets.size();
-  std::vector<trpa_segment> segs;
-  std::vector<trpa_candidate> cands;
-  flatten_record_sets(recordsets, q_store_, db_store_, precs, segs, cands);
-  std::vector<trpa_result> res(n);
+void RPAPredictionModelGPU::predictFlat(const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands,
+                                        uint32_t n_cands, trpa_result* res) {
+  const size_t n = n_segs;
+  if (!n) return;
   // shard contiguous segment ranges over the GPUs, balanced by candidate count; no collective
   const size_t G = std::min(ctx_.size(), std::max<size_t>(1, n));
   std::vector<size_t> cut(G + 1, n);
   cut[0] = 0;
   {
-    const uint64_t total = cands.size() + n;
+    const uint64_t total = (uint64_t)n_cands + n;
     size_t g = 1;
     uint64_t acc = 0;
     for (size_t i = 0; i < n && g < G; ++i) {
@@ -142,17 +139,31 @@ void RPAPredictionModelGPU::predictBatch(std::vector<RecordSet>& recordsets, std
     }
   }
   std::vector<std::string> errors(G);
-  std::vector<std::thread> th;
-  for (size_t g = 0; g < G; ++g) {
-    const size_t b = cut[g], e = cut[g + 1];
-    if (e <= b) continue;
-    const uint32_t cb = segs[b].cand_begin;
-    const uint32_t ce = e < n ? segs[e].cand_begin : (uint32_t)cands.size();
-    th.emplace_back(&RPAPredictionModelGPU::run_shard, this, g, segs.data() + b, (uint32_t)(e - b), cands.data(), cb,
-                    ce - cb, res.data() + b, &errors[g]);
+  if (G == 1) {
+    if (trpa_predict_batch(ctx_[0], segs, n_segs, cands, n_cands, res)) errors[0] = trpa_last_error();
+  } else {
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; ++g) {
+      const size_t b = cut[g], e = cut[g + 1];
+      if (e <= b) continue;
+      const uint32_t cb = segs[b].cand_begin;
+      const uint32_t ce = e < n ? segs[e].cand_begin : n_cands;
+      th.emplace_back(&RPAPredictionModelGPU::run_shard, this, g, segs + b, (uint32_t)(e - b), cands, cb, ce - cb, res + b,
+                      &errors[g]);
+    }
+    for (auto& t : th) t.join();
   }
-  for (auto& t : th) t.join();
   for (const auto& e : errors) if (!e.empty()) throw TaxatorError("GPU prediction failed: " + e);
+}
+
+void RPAPredictionModelGPU::predictBatch(std::vector<RecordSet>& recordsets, std::vector<PredictionRecord>& precs,
+                                         std::ostream& logsink) {
+  const size_t n = recordsets.size();
+  std::vector<trpa_segment> segs;
+  std::vector<trpa_candidate> cands;
+  flatten_record_sets(recordsets, q_store_, db_store_, precs, segs, cands);
+  std::vector<trpa_result> res(n);
+  predictFlat(segs.data(), (uint32_t)n, cands.data(), (uint32_t)cands.size(), res.data());
   apply_results(*tax_, segs, res, precs, logsink, &stats_);
 }
 

@@ -91,8 +91,14 @@ class RPAPredictionModelGPU : public TaxonPredictionModel<RecordSet> {
   // (only matters for n==0 sets, whose ival the reference leaves untouched)
   void predictBatch(std::vector<RecordSet>& recordsets, std::vector<PredictionRecord>& precs, std::ostream& logsink);
 
+  // the flat tables of the C ABI in, result records out: segments sharded over the model's GPUs
+  // (what the fast ingest path of the CLI calls; ingest.h)
+  void predictFlat(const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands, uint32_t n_cands,
+                   trpa_result* res);
+
   typedef PredictStats Stats;
   Stats stats() const { return stats_; }
+  Stats& mutable_stats() { return stats_; }
 
  private:
   void run_shard(size_t dev_slot, const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands,

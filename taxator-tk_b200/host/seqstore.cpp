@@ -64,9 +64,17 @@ static SeqStore parse_fasta(const std::string& data, bool id_is_first_word) {
     while (p < n && data[p] != '>') {
       size_t le = data.find('\n', p);
       if (le == std::string::npos) le = n;
-      for (size_t k = p; k < le; ++k) {
-        const char c = data[k];
-        if (c != ' ' && c != '\t' && c != '\r') s.chars.push_back(c);
+      // bulk copy of the line; blanks inside a sequence line are rare and removed afterwards
+      const size_t before = s.chars.size();
+      s.chars.append(data, p, le - p);
+      if (memchr(s.chars.data() + before, ' ', le - p) || memchr(s.chars.data() + before, '\t', le - p) ||
+          memchr(s.chars.data() + before, '\r', le - p)) {
+        size_t w = before;
+        for (size_t k = before; k < s.chars.size(); ++k) {
+          const char c = s.chars[k];
+          if (c != ' ' && c != '\t' && c != '\r') s.chars[w++] = c;
+        }
+        s.chars.resize(w);
       }
       p = le == n ? n : le + 1;
     }

@@ -3,11 +3,13 @@
 // loop) with the GPU batch predictor swapped for the oracle (oracle/rpa_oracle.cpp).  Run on the
 // same files as the real reference, its GFF3 must be identical -- checks the host logic without a
 // GPU.  Usage: host_cli_harness <nucleotide|protein> mapping query.fna ref.fna ref.fna.fai [batch] [split] [sorted]
+//        [fast_block_bytes]   (> 0: the fast ingest path of the CLI, ingest.h, with that block size)
 #include <cstring>
 #include <fstream>
 #include <iostream>
 
 #include "../taxator-tk_b200/host/driver.h"
+#include "../taxator-tk_b200/host/ingest.h"
 
 extern "C" {
 struct OrcResult {
@@ -42,6 +44,29 @@ int main(int argc, char** argv) {
     std::vector<uint8_t> qc(q.chars.size()), rc(r.chars.size());
     for (size_t i = 0; i < qc.size(); ++i) qc[i] = (uint8_t)(protein ? orc_char2aa((unsigned char)q.chars[i]) : orc_char2dna5((unsigned char)q.chars[i]));
     for (size_t i = 0; i < rc.size(); ++i) rc[i] = (uint8_t)(protein ? orc_char2aa((unsigned char)r.chars[i]) : orc_char2dna5((unsigned char)r.chars[i]));
+    const size_t fast_bytes = argc > 9 ? std::stoul(argv[9]) : 0;
+    auto oracle_segment = [&](uint32_t query_seq, const trpa_candidate* c, uint32_t n, trpa_result* out) {
+      OrcResult o;
+      orc_predict_segment(tax.parent.data(), tax.left.data(), tax.right.data(), tax.depth.data(), (uint32_t)tax.size(),
+                          tax.root, qc.data(), q.off.data(), q.len.data(), (uint32_t)q.size(), rc.data(), r.off.data(),
+                          r.len.data(), (uint32_t)r.size(), protein ? 1 : 0, 0.5f, 0.05f, query_seq, c, n, &o, nullptr, 0,
+                          nullptr);
+      memcpy(out, &o, sizeof(o));
+    };
+    if (fast_bytes) {
+      IngestOptions io;
+      io.split = split;
+      io.block_bytes = fast_bytes;
+      io.threads = 4;
+      io.min_parallel_bytes = 2048;   // exercise the chunked parallel parser on small fixtures
+      run_prediction_fast(
+          stdin, mapping, tax, q, r, io,
+          [&](const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands, uint32_t, trpa_result* res) {
+            for (uint32_t i = 0; i < n_segs; ++i) oracle_segment(segs[i].query_seq, cands + segs[i].cand_begin, segs[i].cand_count, &res[i]);
+          },
+          std::cout, nullptr, nullptr);
+      return 0;
+    }
     RecordSetReader reader(std::cin, mapping, tax, split, sorted);
     std::ofstream nolog("/dev/null");
     run_prediction_stream(

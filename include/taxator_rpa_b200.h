@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TRPA_ABI_VERSION 2
+#define TRPA_ABI_VERSION 3
 
 #define TRPA_OK 0
 #define TRPA_ERR_CUDA (-1)
@@ -135,6 +135,16 @@ int trpa_load_taxonomy(trpa_ctx* ctx, const uint32_t* parent, const uint32_t* le
  * start and length of sequence i.  Packed on the GPU into the HBM-resident store. */
 int trpa_load_store(trpa_ctx* ctx, int store, int alphabet, const char* chars, const uint64_t* off,
                     const uint32_t* len, uint32_t n_seq);
+
+/* Packed stores (the refpack file format of the host): the HBM layout that
+ * trpa_load_store builds -- NT: n_words x {uint32 low-bit plane, uint32 high-bit plane} followed by
+ * n_words x uint32 "is N" plane, every sequence starting on a 32-base word; AA: n_words x uint32 with
+ * six 5-bit ordinals each -- read back to the host once and loaded again without the FASTA / ASCII
+ * detour.  woff has n_seq + 1 entries (word offset of every sequence, then n_words). */
+int trpa_store_info(trpa_ctx* ctx, int store, int* alphabet, uint32_t* n_seq, uint64_t* n_words);
+int trpa_export_store(trpa_ctx* ctx, int store, uint64_t* woff, uint32_t* len, void* payload);
+int trpa_load_store_packed(trpa_ctx* ctx, int store, int alphabet, const uint64_t* woff, const uint32_t* len,
+                           uint32_t n_seq, const void* payload, uint64_t n_words);
 
 /* ---- the hot path ----------------------------------------------------------------------- */
 /* All segments of a batch, host buffers in / host buffers out; == predict() per segment. */

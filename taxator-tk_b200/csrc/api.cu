@@ -614,6 +614,76 @@ int trpa_load_store(trpa_ctx* c, int store, int alphabet, const char* chars, con
   return 0;
 }
 
+// ---- packed stores: what trpa_load_store built, out of and back into HBM without the ASCII detour
+int trpa_store_info(trpa_ctx* c, int store, int* alphabet, uint32_t* n_seq, uint64_t* n_words) {
+  if (!c || store < 0 || store > 1 || !alphabet || !n_seq || !n_words) { set_error("bad arguments"); return TRPA_ERR_ARG; }
+  const Store& S = c->store[store];
+  if (S.alphabet < 0) { set_error("store not loaded"); return TRPA_ERR_STATE; }
+  *alphabet = S.alphabet; *n_seq = S.n_seq; *n_words = S.n_words;
+  return 0;
+}
+
+int trpa_export_store(trpa_ctx* c, int store, uint64_t* woff, uint32_t* len, void* payload) {
+  if (!c || store < 0 || store > 1 || !woff || !len || !payload) { set_error("bad arguments"); return TRPA_ERR_ARG; }
+  if (use_device(c)) return TRPA_ERR_CUDA;
+  const Store& S = c->store[store];
+  if (S.alphabet < 0) { set_error("store not loaded"); return TRPA_ERR_STATE; }
+  CK(cudaMemcpyAsync(woff, S.woff.p, 8ull * (S.n_seq + 1), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(len, S.len.p, 4ull * S.n_seq, cudaMemcpyDeviceToHost, c->stream));
+  uint8_t* out = (uint8_t*)payload;
+  if (S.alphabet == TRPA_ALPHA_NT) {
+    CK(cudaMemcpyAsync(out, S.planes.p, 8ull * S.n_words, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out + 8ull * S.n_words, S.nplane.p, 4ull * S.n_words, cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    CK(cudaMemcpyAsync(out, S.packed.p, 4ull * S.n_words, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int trpa_load_store_packed(trpa_ctx* c, int store, int alphabet, const uint64_t* woff, const uint32_t* len,
+                           uint32_t n_seq, const void* payload, uint64_t n_words) {
+  if (!c || store < 0 || store > 1 || (alphabet != TRPA_ALPHA_NT && alphabet != TRPA_ALPHA_AA) ||
+      (n_seq && (!woff || !len)) || (n_words && !payload)) {
+    set_error("bad store arguments"); return TRPA_ERR_ARG;
+  }
+  // the word offsets must describe word-aligned, non-overlapping sequences in order
+  const u64 per = alphabet == TRPA_ALPHA_NT ? 32 : 6;
+  u64 expect = 0; u32 maxlen = 0;
+  for (u32 i = 0; i < n_seq; ++i) {
+    if (woff[i] != expect) { set_error("packed store: word offsets are not contiguous"); return TRPA_ERR_ARG; }
+    expect += ((u64)len[i] + per - 1) / per;
+    maxlen = std::max(maxlen, len[i]);
+  }
+  if (expect != n_words || (n_seq && woff[n_seq] != n_words)) { set_error("packed store: word count does not match the lengths"); return TRPA_ERR_ARG; }
+  if (alphabet == TRPA_ALPHA_NT && n_words >= 0xffffffffull) { set_error("nucleotide store larger than 2^32 words is not supported yet"); return TRPA_ERR_ARG; }
+  if (use_device(c)) return TRPA_ERR_CUDA;
+  Store& S = c->store[store];
+  S.release();
+  if (S.woff.ensure(n_seq + 1) || S.len.ensure(n_seq + 1)) return TRPA_ERR_NOMEM;
+  const u64 zero = 0;
+  CK(cudaMemcpyAsync(S.woff.p, n_seq ? woff : &zero, 8ull * (n_seq + 1), cudaMemcpyHostToDevice, c->stream));
+  if (n_seq) CK(cudaMemcpyAsync(S.len.p, len, 4ull * n_seq, cudaMemcpyHostToDevice, c->stream));
+  const uint8_t* in = (const uint8_t*)payload;
+  if (alphabet == TRPA_ALPHA_NT) {
+    if (S.planes.ensure(n_words + 2) || S.nplane.ensure(n_words + 2)) return TRPA_ERR_NOMEM;
+    CK(cudaMemsetAsync(S.planes.p + n_words, 0, 2 * sizeof(uint2), c->stream));
+    CK(cudaMemsetAsync(S.nplane.p + n_words, 0, 2 * sizeof(u32), c->stream));
+    if (n_words) {
+      CK(cudaMemcpyAsync(S.planes.p, in, 8ull * n_words, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpyAsync(S.nplane.p, in + 8ull * n_words, 4ull * n_words, cudaMemcpyHostToDevice, c->stream));
+    }
+  } else {
+    if (S.packed.ensure(n_words + 2)) return TRPA_ERR_NOMEM;
+    CK(cudaMemsetAsync(S.packed.p + n_words, 0, 2 * sizeof(u32), c->stream));
+    if (n_words) CK(cudaMemcpyAsync(S.packed.p, in, 4ull * n_words, cudaMemcpyHostToDevice, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  S.alphabet = alphabet; S.n_seq = n_seq; S.n_words = n_words; S.max_len = maxlen;
+  c->batch_ready = false;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------ the hot path
 int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands,
                       uint32_t n_cands) {

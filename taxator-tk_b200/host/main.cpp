@@ -31,6 +31,7 @@ struct Options {
   size_t batch_segments = 200000;
   size_t batch_bytes = 128u << 20;
   bool legacy_ingest = false;
+  std::string write_refpack, write_querypack;
   bool timing = false;
 };
 
@@ -56,6 +57,9 @@ static void usage(std::ostream& os) {
         "  --gpus arg (=0)                   comma separated CUDA device indices to shard segments over\n"
         "  --batch-segments arg (=200000)    record sets per GPU batch (record-at-a-time ingest)\n"
         "  --batch-bytes arg (=134217728)    alignment text per GPU batch (fast ingest)\n"
+        "  --write-refpack arg               write the reference store (-f/-i) as a packed .trpk file and exit;\n"
+        "                                    a .trpk file is accepted wherever a FASTA is (-f, -q)\n"
+        "  --write-querypack arg             same for the query store (-q)\n"
         "  --legacy-ingest                   parse records one at a time like the reference (always used with -o 1)\n"
         "  --timing                          print load/predict timing to stderr\n";
 }
@@ -72,7 +76,7 @@ static int parse_args(int argc, char** argv, Options& o) {
     {"query-sequences", 'q'}, {"query-sequences-index", 'v'}, {"ref-sequences", 'f'}, {"ref-sequences-index", 'i'},
     {"processors", 'p'}, {"logfile", 'l'}, {"dataformat", 'b'}, {"ranks", 'r'}, {"split-alignments", 's'},
     {"alignments-sorted", 'o'}, {"delete-notranks", 'd'}, {"heuristic-cutoff", 'x'}, {"toppercent", 't'},
-    {"gpus", 'G'}, {"batch-segments", 'B'}, {"timing", 'T'}, {"batch-bytes", 'Y'}, {"legacy-ingest", 'L'},
+    {"gpus", 'G'}, {"batch-segments", 'B'}, {"timing", 'T'}, {"batch-bytes", 'Y'}, {"legacy-ingest", 'L'}, {"write-refpack", 'W'}, {"write-querypack", 'Q'},
     // accepted and ignored (other models' knobs)
     {"max-evalue", 'e'}, {"min-support", 'c'}, {"minscore", 'm'}, {"nbest", 'n'}, {"db-whitelist", 'w'},
     {"ignore-unclassified", 'u'}, {"citation", 'C'}, {"advanced-options", 'A'}};
@@ -86,7 +90,7 @@ static int parse_args(int argc, char** argv, Options& o) {
       if (eq != std::string::npos) { val = name.substr(eq + 1); has_val = true; name.resize(eq); }
       for (const auto& s : specs) if (name == s.lng) key = s.shrt;
     } else if (a.size() >= 2 && a[0] == '-') {
-      for (const auto& s : specs) if (a[1] == s.shrt && s.shrt != 'G' && s.shrt != 'B' && s.shrt != 'T' && s.shrt != 'C' && s.shrt != 'A' && s.shrt != 'Y' && s.shrt != 'L') key = s.shrt;
+      for (const auto& s : specs) if (a[1] == s.shrt && s.shrt != 'G' && s.shrt != 'B' && s.shrt != 'T' && s.shrt != 'C' && s.shrt != 'A' && s.shrt != 'Y' && s.shrt != 'L' && s.shrt != 'W' && s.shrt != 'Q') key = s.shrt;
       if (a.size() > 2) { val = a.substr(2); has_val = true; }
     }
     if (!key) throw TaxatorError("unrecognised option '" + a + "'");
@@ -127,6 +131,8 @@ static int parse_args(int argc, char** argv, Options& o) {
       case 'B': o.batch_segments = std::stoul(need()); break;
       case 'Y': o.batch_bytes = std::stoul(need()); break;
       case 'L': o.legacy_ingest = true; break;
+      case 'W': o.write_refpack = need(); break;
+      case 'Q': o.write_querypack = need(); break;
       case 'T': o.timing = true; break;
       case 'u': break;
       default: need(); break;  // ignored options with a value
@@ -168,17 +174,16 @@ int main(int argc, char** argv) {
     const double load_tax_s = secs(t0, ta);
 
     SeqStore q_store;
-    if (opt.query_index.empty()) {
+    if (is_refpack_file(opt.query)) q_store = load_refpack(opt.query);
+    else if (opt.query_index.empty()) {
       std::cerr << "Loading '" << opt.query;
       q_store = load_fasta_inmemory(opt.query);
       std::cerr << "' (total=" << q_store.size() << ")" << std::endl;
     } else q_store = load_fasta_indexed(opt.query, opt.query_index);
-    // the reference store always uses index semantics (ids = first word / .fai name column); the
-    // reference's in-memory mode returns un-reversed whole sequences for reverse hits
-    // (sequencestorage.hh:122-130) and is not reproduced.
     auto tb = std::chrono::steady_clock::now();
     const double load_q_s = secs(ta, tb);
-    SeqStore db_store = load_fasta_indexed(opt.ref, opt.ref_index.empty() ? opt.ref + ".fai" : opt.ref_index);
+    SeqStore db_store = is_refpack_file(opt.ref) ? load_refpack(opt.ref)
+                                                 : load_fasta_indexed(opt.ref, opt.ref_index.empty() ? opt.ref + ".fai" : opt.ref_index);
     auto tc = std::chrono::steady_clock::now();
     const double load_r_s = secs(tb, tc);
 
@@ -186,6 +191,18 @@ int main(int argc, char** argv) {
     RPAPredictionModelGPU model(&tax, q_store, db_store, opt.filterout, opt.toppercent, protein, opt.gpus);
     auto t1 = std::chrono::steady_clock::now();
     const double load_gpu_s = secs(tc, t1);
+    if (!opt.write_refpack.empty() || !opt.write_querypack.empty()) {
+      // the GPU has packed the stores: write them out for later runs and stop
+      for (int which = 0; which < 2; ++which) {
+        const std::string& path = which ? opt.write_refpack : opt.write_querypack;
+        if (path.empty()) continue;
+        std::vector<uint64_t> woff; std::vector<uint32_t> len; std::vector<char> payload; int alphabet = 0;
+        model.exportStore(which, woff, len, payload, alphabet);
+        write_refpack(path, alphabet, which ? db_store.ids : q_store.ids, woff, len, payload);
+        std::cerr << "taxator-b200: wrote " << path << " (" << len.size() << " sequences, " << payload.size() << " packed bytes)" << std::endl;
+      }
+      return EXIT_SUCCESS;
+    }
 
     std::ios::sync_with_stdio(false);
     uint64_t total_sets = 0;

@@ -36,16 +36,36 @@ RPAPredictionModelGPU::RPAPredictionModelGPU(const FlatTaxonomy* tax, const SeqS
     trpa_ctx* c = trpa_create(dev, nullptr);
     if (!c) throw TaxatorError(std::string("GPU context: ") + trpa_last_error());
     ctx_.push_back(c);
+    auto load = [&](int which, const SeqStore& st) -> int {
+      if (st.packed) {   // refpack file: already in the HBM layout
+        if (st.alphabet != alpha) { throw TaxatorError("refpack file holds the other alphabet (-b nucleotide / protein)"); }
+        return trpa_load_store_packed(c, which, alpha, st.woff.data(), st.len.data(), (uint32_t)st.size(), st.payload.data(),
+                                      st.woff.empty() ? 0 : st.woff.back());
+      }
+      return trpa_load_store(c, which, alpha, st.chars.data(), st.off.data(), st.len.data(), (uint32_t)st.size());
+    };
     if (trpa_set_params(c, exclude_factor, reeval_bandwidth) ||
         trpa_load_taxonomy(c, tax->parent.data(), tax->left.data(), tax->right.data(), tax->depth.data(),
                            (uint32_t)tax->size(), tax->root) ||
-        trpa_load_store(c, TRPA_STORE_QUERY, alpha, q_storage.chars.data(), q_storage.off.data(), q_storage.len.data(),
-                        (uint32_t)q_storage.size()) ||
-        trpa_load_store(c, TRPA_STORE_REF, alpha, db_storage.chars.data(), db_storage.off.data(), db_storage.len.data(),
-                        (uint32_t)db_storage.size()))
+        load(TRPA_STORE_QUERY, q_storage) || load(TRPA_STORE_REF, db_storage))
       throw TaxatorError(std::string("GPU set-up: ") + trpa_last_error());
   }
   if (ctx_.empty()) throw TaxatorError("no GPU given");
+}
+
+void RPAPredictionModelGPU::exportStore(int which, std::vector<uint64_t>& woff, std::vector<uint32_t>& len,
+                                        std::vector<char>& payload, int& alphabet) {
+  uint32_t n_seq = 0;
+  uint64_t n_words = 0;
+  if (trpa_store_info(ctx_[0], which, &alphabet, &n_seq, &n_words)) throw TaxatorError(std::string("store export: ") + trpa_last_error());
+  woff.assign((size_t)n_seq + 1, 0);
+  len.assign(n_seq, 0);
+  payload.assign((size_t)(n_words * (alphabet == TRPA_ALPHA_NT ? 12 : 4)), 0);
+  std::vector<uint32_t> len1(std::max<uint32_t>(n_seq, 1));
+  std::vector<char> pay1(std::max<size_t>(payload.size(), 1));
+  if (trpa_export_store(ctx_[0], which, woff.data(), len1.data(), pay1.data())) throw TaxatorError(std::string("store export: ") + trpa_last_error());
+  std::copy(len1.begin(), len1.begin() + n_seq, len.begin());
+  std::copy(pay1.begin(), pay1.begin() + payload.size(), payload.begin());
 }
 
 RPAPredictionModelGPU::~RPAPredictionModelGPU() {

@@ -96,6 +96,9 @@ class RPAPredictionModelGPU : public TaxonPredictionModel<RecordSet> {
   void predictFlat(const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands, uint32_t n_cands,
                    trpa_result* res);
 
+  // a store as the first GPU packed it (what write_refpack() puts into a .trpk file); which = 0 query, 1 reference
+  void exportStore(int which, std::vector<uint64_t>& woff, std::vector<uint32_t>& len, std::vector<char>& payload, int& alphabet);
+
   typedef PredictStats Stats;
   Stats stats() const { return stats_; }
   Stats& mutable_stats() { return stats_; }

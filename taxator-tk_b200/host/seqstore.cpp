@@ -123,4 +123,90 @@ SeqStore load_fasta_indexed(const std::string& fasta, const std::string& fai) {
   return s;
 }
 
+// ------------------------------------------------------------------------------------ refpack file
+namespace {
+const char kRefpackMagic[8] = {'T', 'R', 'P', 'K', 1, 0, 0, 0};
+struct RefpackHeader {
+  char magic[8];
+  uint32_t alphabet, n_seq;
+  uint64_t n_words, ids_bytes, payload_bytes;
+};
+size_t pad8(size_t n) { return (n + 7) & ~(size_t)7; }
+}  // namespace
+
+bool is_refpack_file(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  char m[8];
+  const bool ok = fread(m, 1, 8, f) == 8 && memcmp(m, kRefpackMagic, 8) == 0;
+  fclose(f);
+  return ok;
+}
+
+void write_refpack(const std::string& path, int alphabet, const std::vector<std::string>& ids,
+                   const std::vector<uint64_t>& woff, const std::vector<uint32_t>& len, const std::vector<char>& payload) {
+  if (woff.size() != len.size() + 1 || ids.size() != len.size()) throw TaxatorError("write_refpack: inconsistent tables");
+  std::string idblob;
+  for (const std::string& id : ids) { idblob += id; idblob.push_back('\0'); }
+  RefpackHeader h;
+  memcpy(h.magic, kRefpackMagic, 8);
+  h.alphabet = (uint32_t)alphabet; h.n_seq = (uint32_t)len.size();
+  h.n_words = woff.back(); h.ids_bytes = idblob.size(); h.payload_bytes = payload.size();
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) throw FileError("could not write file: " + path);
+  const char zeros[8] = {0};
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  ok = ok && fwrite(woff.data(), 8, woff.size(), f) == woff.size();
+  ok = ok && (len.empty() || fwrite(len.data(), 4, len.size(), f) == len.size());
+  ok = ok && fwrite(zeros, 1, pad8(4 * len.size()) - 4 * len.size(), f) == pad8(4 * len.size()) - 4 * len.size();
+  ok = ok && (idblob.empty() || fwrite(idblob.data(), 1, idblob.size(), f) == idblob.size());
+  ok = ok && fwrite(zeros, 1, pad8(idblob.size()) - idblob.size(), f) == pad8(idblob.size()) - idblob.size();
+  ok = ok && (payload.empty() || fwrite(payload.data(), 1, payload.size(), f) == payload.size());
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) throw FileError("could not write file: " + path);
+}
+
+SeqStore load_refpack(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) throw FileNotFound("could not find file: " + path);
+  SeqStore s;
+  try {
+    RefpackHeader h;
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, kRefpackMagic, 8) != 0) throw ParsingError("not a refpack file: " + path);
+    if (h.alphabet > 1) throw ParsingError("refpack file with unknown alphabet: " + path);
+    const uint64_t per_word = h.alphabet == 0 ? 12 : 4;
+    if (h.payload_bytes != h.n_words * per_word) throw ParsingError("refpack file is inconsistent: " + path);
+    s.packed = true;
+    s.alphabet = (int)h.alphabet;
+    s.woff.resize((size_t)h.n_seq + 1);
+    std::vector<uint32_t> lens(h.n_seq);
+    std::string idblob((size_t)h.ids_bytes, '\0');
+    s.payload.resize((size_t)h.payload_bytes);
+    char skip[8];
+    bool ok = fread(s.woff.data(), 8, s.woff.size(), f) == s.woff.size();
+    ok = ok && (lens.empty() || fread(lens.data(), 4, lens.size(), f) == lens.size());
+    const size_t p1 = pad8(4 * lens.size()) - 4 * lens.size();
+    ok = ok && (p1 == 0 || fread(skip, 1, p1, f) == p1);
+    ok = ok && (idblob.empty() || fread(&idblob[0], 1, idblob.size(), f) == idblob.size());
+    const size_t p2 = pad8(idblob.size()) - idblob.size();
+    ok = ok && (p2 == 0 || fread(skip, 1, p2, f) == p2);
+    ok = ok && (s.payload.empty() || fread(s.payload.data(), 1, s.payload.size(), f) == s.payload.size());
+    if (!ok || s.woff.back() != h.n_words) throw ParsingError("refpack file is truncated or inconsistent: " + path);
+    size_t p = 0;
+    uint64_t off = 0;
+    for (uint32_t i = 0; i < h.n_seq; ++i) {
+      const size_t e = idblob.find('\0', p);
+      if (e == std::string::npos) throw ParsingError("refpack file has too few identifiers: " + path);
+      add_record(s, idblob.substr(p, e - p), off, lens[i]);   // off: position in the (virtual) residue stream
+      off += lens[i];
+      p = e + 1;
+    }
+  } catch (...) {
+    fclose(f);
+    throw;
+  }
+  fclose(f);
+  return s;
+}
+
 }  // namespace taxator_b200

@@ -34,7 +34,7 @@ class Profile(ctypes.Structure):
 
 
 EXPORTS = ["trpa_abi_version", "trpa_last_error", "trpa_create", "trpa_destroy", "trpa_set_params",
-           "trpa_set_arena_bytes", "trpa_set_lookahead", "trpa_set_band", "trpa_set_tuning", "trpa_profile_reset", "trpa_profile_get", "trpa_load_taxonomy", "trpa_load_store",
+           "trpa_set_arena_bytes", "trpa_set_lookahead", "trpa_set_band", "trpa_set_tuning", "trpa_profile_reset", "trpa_profile_get", "trpa_load_taxonomy", "trpa_load_store", "trpa_store_info", "trpa_export_store", "trpa_load_store_packed",
            "trpa_predict_batch", "trpa_batch_upload", "trpa_batch_run", "trpa_batch_download",
            "trpa_edit_distance_batch", "trpa_protein_align_batch", "trpa_fetch_segments", "trpa_lca_batch",
            "trpa_int_alu_peak"]
@@ -117,6 +117,21 @@ class Context:
         lens = np.ascontiguousarray(lens, np.uint32)
         self._ck(self.L.trpa_load_store(self.h, int(store), int(alphabet), _p(chars), _p(off), _p(lens),
                                         ctypes.c_uint32(len(lens))))
+
+    def export_store(self, store):
+        """(alphabet, woff[n+1], len[n], payload bytes) of a loaded store in its packed HBM layout."""
+        alpha = ctypes.c_int(0); n_seq = ctypes.c_uint32(0); n_words = ctypes.c_uint64(0)
+        self._ck(self.L.trpa_store_info(self.h, int(store), ctypes.byref(alpha), ctypes.byref(n_seq), ctypes.byref(n_words)))
+        woff = np.zeros(n_seq.value + 1, np.uint64); lens = np.zeros(max(n_seq.value, 1), np.uint32)
+        payload = np.zeros(max(1, n_words.value * (12 if alpha.value == 0 else 4)), np.uint8)
+        self._ck(self.L.trpa_export_store(self.h, int(store), _p(woff), _p(lens), _p(payload)))
+        return alpha.value, woff, lens[:n_seq.value], payload[:n_words.value * (12 if alpha.value == 0 else 4)]
+
+    def load_store_packed(self, store, alphabet, woff, lens, payload):
+        woff = np.ascontiguousarray(woff, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
+        payload = np.ascontiguousarray(payload, np.uint8)
+        self._ck(self.L.trpa_load_store_packed(self.h, int(store), int(alphabet), _p(woff), _p(lens), ctypes.c_uint32(len(lens)),
+                                               _p(payload), ctypes.c_uint64(int(woff[-1]) if len(woff) else 0)))
 
     def predict_batch(self, segs, cands):
         segs = np.ascontiguousarray(segs, SEG_DTYPE); cands = np.ascontiguousarray(cands, CAND_DTYPE)

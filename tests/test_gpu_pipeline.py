@@ -91,3 +91,34 @@ def test_fetch_and_lca(ctx):
         w = O.orc_lca(ol.ptr(fd.parent, ol.u32p), ol.ptr(fd.left, ol.u32p), ol.ptr(fd.right, ol.u32p),
                       ol.ptr(fd.depth, ol.u8p), len(fd.parent), 0, int(x[k]), int(y[k]))
         assert g[k] == w
+
+
+def test_packed_store_roundtrip(ctx):
+    """trpa_export_store / trpa_load_store_packed: the HBM layout out and back in gives the same
+    segments (fetch) and the same placements as loading the characters."""
+    import edge_data
+    for fd in (edge_data.n_rich(), edge_data.base(seed=31, protein=True)):
+        alpha = 1 if fd.protein else 0
+        ctx.load_taxonomy(fd.parent, fd.left, fd.right, fd.depth, 0)
+        ctx.load_store(0, alpha, fd.q_chars, fd.q_off, fd.q_len)
+        ctx.load_store(1, alpha, fd.r_chars, fd.r_off, fd.r_len)
+        want = ctx.predict_batch(fd.segs, fd.cands)
+        c = fd.cands[:200]
+        ext = np.zeros(len(c), np.uint32)
+        seg_want = ctx.fetch_segments(c["ref_seq"], c["rstart"], c["rstop"], ext, ext + 7)
+        packs = [ctx.export_store(0), ctx.export_store(1)]
+        assert packs[0][0] == alpha and len(packs[1][2]) == len(fd.r_len)
+        # load something else in between, then the packed copies
+        ctx.load_store(0, alpha, fd.q_chars[:1], fd.q_off[:1], np.ones(1, np.uint32))
+        ctx.load_store(1, alpha, fd.r_chars[:1], fd.r_off[:1], np.ones(1, np.uint32))
+        for which, (a, woff, lens, payload) in enumerate(packs):
+            ctx.load_store_packed(which, a, woff, lens, payload)
+        got = ctx.predict_batch(fd.segs, fd.cands)
+        assert ol.results_equal(want, got) == []
+        seg_got = ctx.fetch_segments(c["ref_seq"], c["rstart"], c["rstop"], ext, ext + 7)
+        assert all(np.array_equal(x, y) for x, y in zip(seg_want, seg_got))
+        # a payload that does not match its tables is rejected
+        import rpa_b200
+        a, woff, lens, payload = packs[1]
+        with pytest.raises(rpa_b200.TrpaError):
+            ctx.load_store_packed(1, a, woff + np.uint64(1), lens, payload)

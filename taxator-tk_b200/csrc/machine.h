@@ -195,7 +195,7 @@ struct Machine {
     for (uint32_t j = j0; budget && j < S.n && rec[j].score >= S.score_thr_i; ++j) {
       if (j == S.anchor || qd[j] == .0f) continue;
       if (!(static_cast<double>(qsim[j]) / S.qrlength >= thr)) continue;
-      if (B.tag[S.cbeg + j] == S.anchor + 1u) continue;
+      if (pair_slot(j, S.anchor) != 0xffffffffu) continue;
       stage_candidate(j);
       emit_pair(desc_cand(j), desc_cand(S.anchor), S.cbeg + j, hint_pair(j, S.anchor));
       B.tag[S.cbeg + j] = S.anchor + 1u;
@@ -209,7 +209,7 @@ struct Machine {
       if (!(static_cast<double>(qsim[j]) / S.qrlength >= S.qpid_thresh2)) continue;
       const uint32_t cnode = rec[j].node;
       if (tx_is_parent_of(B.tax, S.unode_g, cnode) || cnode == S.unode_g) continue;
-      if (B.tag[S.cbeg + j] == S.anchor + 1u) continue;
+      if (pair_slot(j, S.anchor) != 0xffffffffu) continue;
       stage_candidate(j);
       emit_pair(desc_cand(j), desc_cand(S.anchor), S.cbeg + j, hint_pair(j, S.anchor));
       B.tag[S.cbeg + j] = S.anchor + 1u;
@@ -217,6 +217,15 @@ struct Machine {
     }
   }
   TRPA_HD uint32_t desc_cand(uint32_t i) const { return B.n_segs + S.cbeg + i; }
+  // Result slot that already holds the alignment of segment i with segment `anchor`, or ~0: record
+  // i's own slot (tag = anchor + 1: computed for this anchor by pass 1, pass 2 or look-ahead) or --
+  // nucleotide only, the edit distance and the derived match count are symmetric -- the slot of
+  // `anchor` when that record was itself aligned against i while i was the anchor.
+  TRPA_HD uint32_t pair_slot(uint32_t i, uint32_t anchor) const {
+    if (B.tag[S.cbeg + i] == anchor + 1u) return S.cbeg + i;
+    if (!B.protein && B.tag[S.cbeg + anchor] == i + 1u) return S.cbeg + anchor;
+    return 0xffffffffu;
+  }
 
   // distance/similarity of a finished alignment (hh:133-171 / hh:173-242)
   TRPA_HD void read_alignment(uint32_t slot, uint32_t da, uint32_t db, float& dist, float& sim) const {
@@ -463,9 +472,9 @@ struct Machine {
           if (take) {
             if (i == S.anchor) dist = .0f;
             else if (qd[i] == .0f) dist = qd[S.anchor];
-            else if (B.tag[S.cbeg + i] == S.anchor + 1u) {  // already computed by look-ahead
+            else if (pair_slot(i, S.anchor) != 0xffffffffu) {  // already computed (look-ahead, or as anchor <-> i)
               float sim;
-              read_alignment(S.cbeg + i, desc_cand(i), desc_cand(S.anchor), dist, sim);
+              read_alignment(pair_slot(i, S.anchor), desc_cand(i), desc_cand(S.anchor), dist, sim);
               count_cells(desc_cand(i), desc_cand(S.anchor));
               ++S.c1;
             } else {
@@ -583,9 +592,9 @@ struct Machine {
             const uint32_t cnode = rec[i].node;
             if (i == anchor) dist = .0f;
             else if (tx_is_parent_of(T, S.unode_g, cnode) || cnode == S.unode_g) take = false;  // "continue"
-            else if (B.tag[S.cbeg + i] == anchor + 1u) {  // already computed (look-ahead or pass 1)
+            else if (pair_slot(i, anchor) != 0xffffffffu) {  // already computed (look-ahead, pass 1, or as anchor <-> i)
               float sim;
-              read_alignment(S.cbeg + i, desc_cand(i), desc_cand(anchor), dist, sim);
+              read_alignment(pair_slot(i, anchor), desc_cand(i), desc_cand(anchor), dist, sim);
               count_cells(desc_cand(i), desc_cand(anchor));
               ++S.c2;
               qd[i] = dist;

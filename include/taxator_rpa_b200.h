@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TRPA_ABI_VERSION 3
+#define TRPA_ABI_VERSION 4
 
 #define TRPA_OK 0
 #define TRPA_ERR_CUDA (-1)
@@ -97,7 +97,8 @@ typedef struct trpa_profile {
   double ms_other;          uint64_t launches_other;
   uint64_t rounds;
   uint64_t pairs;
-  uint64_t band_retries;          /* pairs re-run with a wider band (first threshold was too small) */
+  uint64_t band_retries;          /* pairs re-run (threshold too small, or a wedge whose certificate failed) */
+  uint64_t wedge_failures;        /* of those: wedges whose certificate failed */
 } trpa_profile;
 
 /* ---- lifecycle --------------------------------------------------------------------------- */
@@ -119,7 +120,8 @@ int trpa_set_lookahead(trpa_ctx* ctx, int k);
  * cells.  0 = the full DP matrix like the reference's bit-vector loop (A/B runs). */
 int trpa_set_band(trpa_ctx* ctx, int on);
 /* Test / tuning hooks (results never depend on them): "band_k0" = forced initial band threshold
- * (exercises the verify-and-widen loop), "plan_lanes" = lanes the shape planner assumes,
+ * (exercises the verify-and-widen loop), "wedge" = 0 keeps the band at constant width (1: let it narrow
+ * where the kernel's certificate proves that exact), "plan_lanes" = lanes the shape planner assumes,
  * "myers_version" = 2 selects the previous full-matrix kernel for A/B runs. */
 int trpa_set_tuning(trpa_ctx* ctx, const char* key, int64_t value);
 int trpa_profile_reset(trpa_ctx* ctx);

@@ -29,9 +29,13 @@ def popc(x):
 
 
 class Geometry:
-    """Band geometry shared by the model and (re-implemented in) the kernel."""
+    """Band geometry shared by the model and (re-implemented in) the kernel.
 
-    def __init__(self, m, n, k, W, L):
+    a1 (optional) turns the band into a WEDGE: the half width shrinks linearly from a0 = (k - delta) / 2
+    at the first pattern row to a1 at the last one (errors accumulate along the alignment, so far-off
+    cells stop being useful towards the end).  A wedge result is only accepted with a certificate."""
+
+    def __init__(self, m, n, k, W, L, a1=None, x0=0):
         assert m <= n and m > 0
         self.m, self.n, self.W, self.L = m, n, W, L
         self.R = 32 * W
@@ -39,16 +43,29 @@ class Geometry:
         k = max(k, self.delta + 64)
         k = min(k, max(n, self.delta + 64))
         self.k = k
-        self.a = (k - self.delta) // 2          # half band width below the main diagonal (>= 32)
+        self.a0 = (k - self.delta) // 2          # half band width at the first row (>= 32)
+        self.a1 = self.a0 if a1 is None else max(32, min(self.a0, a1))
+        self.row0 = self.a0 + x0                 # the wedge keeps the full width up to this row
+        self.wedge = self.a1 < self.a0 and m > self.row0 + 64
+        if not self.wedge:
+            self.a1 = self.a0
         self.mwords = (m + 31) // 32
         self.nblk = (n + 31) // 32
         self.S = (self.mwords + W - 1) // W
 
+    def a(self, s):
+        # full width up to row0 (a cell at offset a has only seen row - a columns, and the number of errors
+        # seen so far fluctuates), then linear
+        row = min(s * self.R, self.m)
+        if not self.wedge or row <= self.row0:
+            return self.a0
+        return self.a0 - ((self.a0 - self.a1) * (row - self.row0)) // (self.m - self.row0)
+
     def b0(self, s):
-        return max(0, s * self.R - self.a) // 32
+        return max(0, s * self.R - self.a(s)) // 32
 
     def b1(self, s):
-        return min(self.n - 1, (s + 1) * self.R - 1 + self.delta + self.a) // 32
+        return min(self.n - 1, (s + 1) * self.R - 1 + self.delta + self.a(s)) // 32
 
     def round_gap(self, r):
         """Extra steps between round r and r+1 (Delta_r >= 1 when a next round exists)."""
@@ -61,10 +78,14 @@ class Geometry:
         return g
 
 
-def banded_distance(pat, txt, k, W, L, stats=None):
-    """Returns (v, k_used): v >= d, and v == d if v <= k_used."""
+def banded_distance(pat, txt, k, W, L, stats=None, a1=None, x0=0):
+    """Returns (v, k_used, cert): v >= d always; v == d if v <= k_used and (no wedge or cert >= v).
+
+    cert = min over the cells through which a path can leave the computed region of (value + remaining
+    diagonal distance): a path that leaves costs at least that much, so cert >= v proves that no path
+    outside the region beats v."""
     m, n = len(pat), len(txt)
-    G = Geometry(m, n, k, W, L)
+    G = Geometry(m, n, k, W, L, a1, x0)
     R, S, nblk = G.R, G.S, G.nblk
     maskR = (1 << R) - 1
     sigma = sorted(set(pat) | set(txt))
@@ -85,6 +106,14 @@ def banded_distance(pat, txt, k, W, L, stats=None):
         ln.off = 0             # offset_r of the lane's current round
         ln.r = 0
     result = None
+    cert = 1 << 60
+    delta = G.delta
+    if G.b1(0) < nblk - 1:      # along row 0 past strip 0's range: D[0][j] = j, back to diagonal delta
+        cert = min(cert, 2 * 32 * (G.b1(0) + 1) - delta)
+    for s1 in range(1, S):      # down column 0 to the first strip that does not start at column 0
+        if G.b0(s1) > 0:
+            cert = min(cert, 2 * (s1 * R + 1) + delta)
+            break
     t = 0
     blocks_done = 0
     while True:
@@ -156,6 +185,17 @@ def banded_distance(pat, txt, k, W, L, stats=None):
             blocks_done += 1
             ln.botacc += popc(hp_out) - popc(hn_out)
             ln.out = (hp_out, hn_out, c_out, ln.botacc)
+            if s + 1 < S:
+                if b < G.b0(s + 1):       # bottom-row cells whose lower neighbours are not computed
+                    term = ln.botacc + ((s + 1) * R - 32 * (b + 1)) + delta
+                    if stats is not None and term < cert:
+                        stats['argmin'] = ('bottom', s, b, ln.botacc, G.a(s), G.a(s + 1))
+                    cert = min(cert, term)
+                if b == ln.b1 and b < nblk - 1:   # right-column cells of the strip
+                    term = ln.botacc + (32 * (b + 1) - (s + 1) * R) - delta
+                    if stats is not None and term < cert:
+                        stats['argmin'] = ('right', s, b, ln.botacc, G.a(s), G.a(s + 1))
+                    cert = min(cert, term)
             if l == L - 1 and s + 1 < S:
                 scratch[b] = ln.out
             if b == ln.b1:
@@ -174,25 +214,30 @@ def banded_distance(pat, txt, k, W, L, stats=None):
         stats["blocks"] = blocks_done
         stats["steps"] = t
         stats["full_blocks"] = S * nblk
-    return result, G.k
+    return result, G.k, (cert if G.wedge else None)
 
 
-def exact_distance(pat, txt, k0, W, L, stats=None):
-    """The retry loop of the kernel: widen k until the banded result is provably exact."""
+def exact_distance(pat, txt, k0, W, L, stats=None, a1=None, x0=0):
+    """The retry loop of the kernel: widen until the banded / wedged result is provably exact."""
     if len(pat) > len(txt):
         pat, txt = txt, pat
     if len(pat) == 0:
         return len(txt)
     k = k0
     tries = 0
+    wedge_fail = 0
     while True:
-        v, ku = banded_distance(pat, txt, k, W, L, stats)
+        v, ku, cert = banded_distance(pat, txt, k, W, L, stats, a1, x0)
         tries += 1
-        if v <= ku:
+        if v <= ku and (cert is None or cert >= v):
             if stats is not None:
                 stats["tries"] = tries
+                stats["wedge_fail"] = wedge_fail
             return v
-        k = min(v, 3 * ku)
+        if cert is not None:
+            wedge_fail += 1
+        a1 = None                      # second attempts use the plain band
+        k = ku if v <= ku else min(v, 3 * ku)
 
 
 def _rand_pair(rng, m, div, indel):
@@ -226,8 +271,9 @@ def main():
         k0 = rng.choice([0, 1, 10, 50, 100, 400, 10 ** 6])
         want = dp_distance(a, b)
         st = {}
-        got = exact_distance(a, b, k0, W, L, st)
-        assert got == want, (it, len(a), len(b), W, L, k0, got, want)
+        a1 = rng.choice([None, None, 32, 40, 64, 100, 200])
+        got = exact_distance(a, b, k0, W, L, st, a1, rng.choice([0, 0, 64, 200]))
+        assert got == want, (it, len(a), len(b), W, L, k0, a1, got, want)
         if st:
             worst = max(worst, st["blocks"] / max(1, st["full_blocks"]))
     print("band model ok: %d cases" % n_cases)

@@ -155,6 +155,7 @@ struct trpa_ctx {
   DevBuf<uint8_t> arena_aa;
   u64 arena_units = 0;
   int band = 1;               // 1: Ukkonen band (exact), 0: full DP matrix
+  int wedge = 1;              // 1: let the band narrow along the matrix where a certificate can prove it (exact)
   int myers_version = 3;      // 3: banded rotating-strip kernel, 2: myers2 (A/B runs, TRPA_MYERS=2)
   // pipes: independent sub-batch pipelines whose rounds overlap on the GPU (pipe[0] runs on `stream`)
   static constexpr int kMaxPipes = 4;
@@ -291,8 +292,8 @@ int Pipe::init(cudaStream_t user_stream) {
     own_stream = true;
   }
   CK(cudaMallocHost(&h_counters, sizeof(u32) * (kNumCounters + 2 * kNumShapes)));
-  if (d_counters.ensure(kNumCounters) || d_hist.ensure(3 * kNumShapes) || d_buckets.ensure(kNumShapes) || d_plan.ensure(4)) return TRPA_ERR_NOMEM;
-  CK(cudaMemsetAsync(d_plan.p, 0, 4 * sizeof(unsigned long long), stream));
+  if (d_counters.ensure(kNumCounters) || d_hist.ensure(3 * kNumShapes) || d_buckets.ensure(kNumShapes) || d_plan.ensure(8)) return TRPA_ERR_NOMEM;
+  CK(cudaMemsetAsync(d_plan.p, 0, 8 * sizeof(unsigned long long), stream));
   CK(cudaStreamSynchronize(stream));
   ready = true;
   return 0;
@@ -366,7 +367,7 @@ static int bucket_pairs3(trpa_ctx* c, Pipe& P, PairDesc* pairs, u32 n_pairs, con
   CK(cudaMemsetAsync(P.d_hist.p, 0, sizeof(u32) * 3 * kNumShapes, P.stream));
   const u32 blocks = std::min<u32>((n_pairs + 255) / 256, 148 * 8);
   CK(launch_plan(pairs, n_pairs, descs, planes, nplane, P.d_hist.p, c->plan_lanes ? c->plan_lanes : (u32)c->num_sms * 16u * 32u,
-                 c->band ? (c->band_k0 ? (int)c->band_k0 : 1) : 0, c->force_shape, P.stream));
+                 c->band ? (c->band_k0 ? (int)c->band_k0 : 1) : 0, c->force_shape, c->wedge, P.stream));
   scan_kernel<<<1, 32, 0, P.stream>>>(P.d_hist.p, P.d_buckets.p);
   scatter_kernel<<<blocks, 256, 0, P.stream>>>(pairs, n_pairs, P.d_hist.p, sorted);
   CK(cudaGetLastError());
@@ -453,12 +454,13 @@ static int launch_myers_shapes3(trpa_ctx* c, Pipe& P, const u32* h_hist, const P
 // {word-blocks, retries, pairs} of the banded kernel since the last call -> profile
 static int harvest_band_stats(trpa_ctx* c, Pipe& P) {
   if (!P.d_plan.p) return 0;
-  unsigned long long h[3] = {0, 0, 0};
+  unsigned long long h[4] = {0, 0, 0, 0};
   CK(cudaMemcpyAsync(h, P.d_plan.p + 1, sizeof(h), cudaMemcpyDeviceToHost, P.stream));
   CK(cudaStreamSynchronize(P.stream));
   CK(cudaMemsetAsync(P.d_plan.p + 1, 0, sizeof(h), P.stream));
   c->prof.cells_edit_distance += h[0] * 1024ull;
   c->prof.band_retries += h[1];
+  c->prof.wedge_failures += h[3];
   return 0;
 }
 
@@ -488,6 +490,7 @@ trpa_ctx* trpa_create(int device, void* cuda_stream) {
   c->own_stream = false;   // owned by pipe[0]
   if (cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->num_sms <= 0) c->num_sms = 148;
   if (const char* e = getenv("TRPA_BAND")) c->band = e[0] != '0';
+  if (const char* e = getenv("TRPA_WEDGE")) c->wedge = e[0] != '0';
   if (const char* e = getenv("TRPA_MYERS")) c->myers_version = e[0] == '2' ? 2 : 3;
   if (const char* e = getenv("TRPA_PIPES")) c->n_pipes = std::max(1, std::min((int)trpa_ctx::kMaxPipes, atoi(e)));
   return c;
@@ -534,6 +537,7 @@ int trpa_set_tuning(trpa_ctx* c, const char* key, int64_t value) {
   if (k == "band_k0") c->band_k0 = value < 0 ? 0u : (u32)std::min<int64_t>(value, 0xfffffe);
   else if (k == "plan_lanes") c->plan_lanes = value < 0 ? 0u : (u32)std::min<int64_t>(value, 1 << 30);
   else if (k == "myers_version") c->myers_version = value == 2 ? 2 : 3;
+  else if (k == "wedge") c->wedge = value < 0 ? 0 : (value > 2 ? 2 : (int)value);   // 2: test hook, see plan_kernel
   else if (k == "la_cap") c->la_cap = (u32)std::max<int64_t>(1, value);
   else if (k == "la_max") c->la_max = (u32)std::max<int64_t>(0, std::min<int64_t>(64, value));
   else if (k == "force_shape") c->force_shape = value < 0 || value >= kNumW * kNumL ? -1 : (int)value;
@@ -1068,7 +1072,7 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   for (u32 i = 0; i < n_seq; ++i) sd[i].flags = h_flags[i];
   CK(cudaMemcpyAsync(d_sd.p, sd.data(), sizeof(SeqDesc) * n_seq, cudaMemcpyHostToDevice, c->stream));
   std::vector<PairDesc> hp(n_pairs);
-  for (u32 k = 0; k < n_pairs; ++k) hp[k] = PairDesc{pair_a[k], pair_b[k], k, 0};
+  for (u32 k = 0; k < n_pairs; ++k) hp[k] = PairDesc{pair_a[k], pair_b[k], k, 0, 0};
   CK(cudaMemcpyAsync(d_pairs.p, hp.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, c->stream));
   std::vector<u32> h_hist(kNumShapes, 0);
   const bool v3 = c->myers_version == 3;
@@ -1128,7 +1132,7 @@ int trpa_protein_align_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   CK(cudaMemcpyAsync(d_sd.p, sd.data(), sizeof(SeqDesc) * n_seq, cudaMemcpyHostToDevice, c->stream));
   CK(launch_selfscore(d_sd.p, n_seq, d_codes.p, c->stream));
   std::vector<PairDesc> hp(n_pairs);
-  for (u32 k = 0; k < n_pairs; ++k) hp[k] = PairDesc{pair_a[k], pair_b[k], k, 0};
+  for (u32 k = 0; k < n_pairs; ++k) hp[k] = PairDesc{pair_a[k], pair_b[k], k, 0, 0};
   CK(cudaMemcpyAsync(d_pairs.p, hp.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, c->stream));
   int2* scr = nullptr; u32 stride = 0;
   if (max_len > 512) {

@@ -163,7 +163,7 @@ struct Machine {
   // which verifies it and widens the band when it was too small: results never depend on it.
   TRPA_HD void emit_pair(uint32_t da, uint32_t db, uint32_t slot, uint32_t hint = 0u) {
     const uint32_t q = TRPA_ATOMIC_ADD_U32(&B.counters[CN_PAIRS], 1u);
-    B.pairs[q] = PairDesc{da, db, slot, hint};
+    B.pairs[q] = PairDesc{da, db, slot, hint, 0u};
   }
   // the aligner's own alignment of record i (alnlen columns, `identities` matches) is an edit script
   // of its query range; scaled to the whole query range of the segment

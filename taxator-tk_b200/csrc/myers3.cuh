@@ -21,6 +21,15 @@
 //  * the score is assembled from deltas: corner(s) (value above the strip at its first column,
 //    handed down the same way) + the top-boundary deltas of the last strip + popc(VP) - popc(VN) of
 //    the last column.
+//  * wedge (PairDesc.aux = half width at the last pattern row, 0 = plain band): errors accumulate along
+//    an alignment, so towards the end of the matrix a cell far from the diagonal cannot lie on a path of
+//    cost <= k any more (its value plus the remaining diagonal distance exceeds k).  The planner
+//    therefore lets the band narrow linearly.  Unlike the plain band a wedge is not exact by
+//    construction; the kernel CERTIFIES it: a path that leaves the computed region does so through a
+//    cell of a strip's bottom row left of the next strip's first column, through a strip's last
+//    column, or along row 0 / column 0, and then still has to come back to the final diagonal, so it
+//    costs at least cert = min over those cells of (computed value + remaining diagonal distance).
+//    cert >= v proves that no such path beats v; otherwise the pair is run again with the plain band.
 // scripts/band_model.py is an executable model of exactly this schedule (checked against a plain DP).
 #pragma once
 #include "myers2.cuh"
@@ -41,7 +50,8 @@ __device__ __forceinline__ void stcg_u4(uint4* p, uint4 v) {
 // (kPadKFull = no band).
 constexpr u32 kPadKFull = 0xffffffu;
 
-// stats[0] += executed 32x32-cell word-blocks, stats[1] += band retries, stats[2] += pairs
+// stats[0] += executed 32x32-cell word-blocks, stats[1] += band retries, stats[2] += pairs,
+// stats[3] += wedges whose certificate failed (re-run with the plain band)
 template <int W, bool HASN>
 __global__ void __launch_bounds__(128)
 myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __restrict__ seqs,
@@ -72,29 +82,39 @@ myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __re
 
   bool active = false, exhausted = !in_group, need_setup = false;
   // pair (uniform inside a group)
-  u32 m = 0, n = 0, pw = 0, tw = 0, oidx = 0, mwords = 0, S = 0, a = 0, ua = 0, k = 0, t = 0;
+  u32 m = 0, n = 0, pw = 0, tw = 0, oidx = 0, mwords = 0, S = 0, k = 0, t = 0;
+  BandGeom bg;   // band / wedge of the current attempt
+  bg.m = bg.n = 1; bg.a0 = bg.a1 = 0; bg.taper_q = 0; bg.k = 0;
   // lane
-  u32 s = 0, r = 0, T0 = 0, sb0 = 0, sb1 = 0, pb1 = 0;
-  int corner = 0, botacc = 0, tsum = 0, vfinal = 0;
+  u32 s = 0, r = 0, T0 = 0, sb0 = 0, sb1 = 0, pb1 = 0, nb0 = 0;
+  int corner = 0, botacc = 0, tsum = 0, vfinal = 0, cert = 0x7fffffff;
   u32 VP[W], VN[W];
   u32 hpOut = 0, hnOut = 0, cOut = 0;
   uint4 pre = make_uint4(0u, 0u, 0u, 0u);
   bool have_pre = false;
-  u32 nblocks = 0, nretry = 0, npairs = 0;
+  u32 nblocks = 0, nretry = 0, npairs = 0, nwfail = 0;
 
-  auto gb0 = [&](u32 st) -> u32 { const u32 x = st * R; return x > a ? (x - a) >> 5 : 0u; };
-  auto gb1 = [&](u32 st) -> u32 { const u32 hi = (st + 1u) * R - 1u + ua; return (hi < n - 1u ? hi : n - 1u) >> 5; };
-  auto set_band = [&](u32 kk) {
-    const BandGeom bg = band_from_k(m, n, kk, force_full != 0);
-    a = bg.a; ua = bg.ua; k = bg.k;
+  auto gb0 = [&](u32 st) -> u32 { return bg.b0(st, R); };
+  auto gb1 = [&](u32 st) -> u32 { return bg.b1(st, R); };
+  auto set_band = [&](u32 kk, u32 a1_req) {
+    bg = band_from_k(m, n, kk, force_full != 0, a1_req);
+    k = bg.k;
   };
   auto start_attempt = [&]() {
     t = 0; s = sl; r = 0; T0 = sl;
     need_setup = s < S;
     hpOut = 0; hnOut = 0; cOut = 0; botacc = 0;
+    cert = 0x7fffffff;
   };
   auto setup_strip = [&]() {
     sb0 = gb0(s); sb1 = gb1(s); pb1 = s ? gb1(s - 1u) : 0u;
+    nb0 = s + 1u < S ? gb0(s + 1u) : 0u;
+    if (bg.wedge()) {   // ways out of the region along the matrix borders (row 0, column 0)
+      const int delta = (int)(n - m);
+      const u32 nblk = (n + 31u) >> 5;
+      if (s == 0 && sb1 + 1u < nblk) cert = min(cert, 64 * (int)(sb1 + 1u) - delta);
+      if (s > 0 && sb0 > 0 && gb0(s - 1u) == 0) cert = min(cert, 2 * (int)(s * R + 1u) + delta);
+    }
     const u32 kbase = s * W;
 #pragma unroll
     for (int q = 0; q < WQ; ++q) {
@@ -153,7 +173,7 @@ myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __re
         } else {
           S = (mwords + W - 1) / W;
           const u32 k0 = pd.pad >> 8;
-          set_band(k0 >= kPadKFull ? 0xffffffffu : k0);
+          set_band(k0 >= kPadKFull ? 0xffffffffu : k0, pd.aux);
           start_attempt();
           active = true;
         }
@@ -233,6 +253,11 @@ myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __re
       ++nblocks;
       botacc += __popc(hpOut) - __popc(hnOut);
       if (sl == (u32)L - 1u && s + 1u < S) stcg_u4(my_scratch + b, make_uint4(hpOut, hnOut, cOut, (u32)botacc));
+      if (bg.wedge() && s + 1u < S) {   // certificate: cells through which a path can leave the region
+        const int delta = (int)(n - m);
+        if (b < nb0) cert = min(cert, botacc + (int)((s + 1u) * R - 32u * (b + 1u)) + delta);
+        if (b == sb1 && 32u * (b + 1u) < n) cert = min(cert, botacc + (int)(32u * (b + 1u) - (s + 1u) * R) - delta);
+      }
       if (b == sb1) {  // strip finished
         if (islast) {
           int acc = corner + tsum;
@@ -260,13 +285,20 @@ myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __re
     const u32 fin = __ballot_sync(0xffffffffu, fin_lane) & gmask;
     if (in_group && fin) {  // uniform inside a group
       const int v = __shfl_sync(gmask, vfinal, __ffs(fin) - 1);
-      if ((u32)v <= k) {
+      bool ok = (u32)v <= k;
+      if (bg.wedge()) {
+        int cm = cert;
+        for (int o = L >> 1; o > 0; o >>= 1) cm = min(cm, __shfl_xor_sync(gmask, cm, o));
+        if (ok && cm < v) { ok = false; if (sl == 0) ++nwfail; }
+      }
+      if (ok) {
         if (sl == 0) out[oidx] = v;
         active = false;
       } else {
-        // d > k proven; v is an upper bound of d
+        // plain band from here on: v <= k means only the certificate failed (the band of k is then
+        // exact); otherwise d > k is proven and v is an upper bound of d
         const u32 k3 = k > 0x55555555u ? 0xffffffffu : 3u * k;
-        set_band((u32)v < k3 ? (u32)v : k3);
+        set_band((u32)v <= k ? k : ((u32)v < k3 ? (u32)v : k3), 0u);
         start_attempt();
         if (sl == 0) ++nretry;
       }
@@ -278,12 +310,14 @@ myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __re
     for (int o = 16; o > 0; o >>= 1) {
       wb += __shfl_xor_sync(0xffffffffu, wb, o);
       nretry += __shfl_xor_sync(0xffffffffu, nretry, o);
+      nwfail += __shfl_xor_sync(0xffffffffu, nwfail, o);
       npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
     }
     if (lane == 0) {
       atomicAdd(&stats[0], wb);
       if (nretry) atomicAdd(&stats[1], (unsigned long long)nretry);
       atomicAdd(&stats[2], (unsigned long long)npairs);
+      if (nwfail) atomicAdd(&stats[3], (unsigned long long)nwfail);
     }
   }
 }

@@ -93,7 +93,7 @@ cudaError_t launch_myers(int shape, const PairDesc* pairs, u32 count, const SeqD
 // when pairs are plentiful, latency when they are scarce).  pad <- shape | k0 << 8; histogram.
 __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const SeqDesc* __restrict__ descs,
                             const uint2* __restrict__ planes, const u32* __restrict__ nplane,
-                            u32* __restrict__ hist, u32 lanes_total, int band, int force_shape) {
+                            u32* __restrict__ hist, u32 lanes_total, int band, int force_shape, int wedge) {
   const u32 lane = threadIdx.x & 31;
   const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -104,29 +104,72 @@ __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const Seq
     if (A.len < B.len) { m = A.len; pw = A.woff; n = B.len; tw = B.woff; }
     else               { m = B.len; pw = B.woff; n = A.len; tw = A.woff; }
     const int hasn = (int)((A.flags | B.flags) & 1u);
-    u32 k0 = kPadKFull;
+    u32 k0 = kPadKFull, a1 = 0;
     if (band && m >= 64u) {
+      // every lane counts the mismatches of one contiguous 1/32 of the pattern, so that the prefix sums
+      // over the lanes give the mismatch profile along the sequence
       const u32 mwords = (m + 31) >> 5;
+      const u32 per = (mwords + 31u) >> 5;
       u32 h = 0;
-      for (u32 w = lane; w < mwords; w += 32) {
+      for (u32 w = lane * per; w < (lane + 1u) * per && w < mwords; ++w) {
         const uint2 x = planes[pw + w], y = planes[tw + w];
         u32 mm = (x.x ^ y.x) | (x.y ^ y.y);
         if (hasn) mm |= nplane[pw + w] ^ nplane[tw + w];
         if (w == mwords - 1 && (m & 31u)) mm &= (1u << (m & 31u)) - 1u;
         h += __popc(mm);
       }
+      u32 cum = h;   // inclusive prefix sum over the lanes
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
-      u32 ub = h + (n - m);                       // a valid alignment: d <= ub
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 v = __shfl_up_sync(0xffffffffu, cum, o);
+        if ((int)lane >= o) cum += v;
+      }
+      const u32 total = __shfl_sync(0xffffffffu, cum, 31);
+      u32 ub = total + (n - m);                   // a valid alignment: d <= ub
       const u32 hint = pd.pad;
+      bool from_hint = false;
       if (hint) {
         const u32 hk = hint + (hint >> 3) + 32u;  // estimate, not a bound: the kernel verifies
-        if (hk < ub) ub = hk;
+        if (hk < ub) { ub = hk; from_hint = true; }
       }
       if (band > 1) ub = (u32)band;               // test hook: forced initial threshold
       k0 = ub < kPadKFull ? ub : kPadKFull - 1u;
+      // wedge: slowest average mismatch rate over any prefix (>= 1/8 of the pattern) as a cautious
+      // estimate of how fast errors accumulate along the alignment; 3/4 of it narrows the band
+      // (measured, scripts/wedge_probe.py: pays from ~8 % divergence and 2 kb on; with half widths beyond
+      // ~1000 the cheapest paths to far-off cells dodge most mismatches and the certificate fails)
+      const bool pays = m >= 2048u && total * 3u < m && total * 12u >= m && total + (n - m) <= 2048u;
+      if (wedge && !from_hint && band == 1 && (wedge == 2 ? m >= 256u : pays)) {
+        const u32 pos = min(m, (lane + 1u) * per * 32u);      // pattern rows covered up to this lane
+        // rate in mismatches per 2^16 rows, rounded down
+        u32 rate = pos * 8u >= m ? (u32)(((uint64_t)cum << 16) / pos) : 0xffffffffu;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rate = min(rate, __shfl_xor_sync(0xffffffffu, rate, o));
+        // A cell at diagonal offset a of row `row` has seen the errors of its first (row - a) columns
+        // only, and the count fluctuates: keep the full width until about 30 errors are expected
+        // (x0 rows after the first a0), then  2 a + s rate (row - a - x0) = k - delta  with s = 3/4
+        //   ->  a(m) = (K - s rate (m - x0)) / (2 - s rate)
+        // (the exit cells of the first strips have seen almost no errors yet: their certificate term is
+        // about k0 itself, so k0 gets a small cushion over the distance bound)
+        const u32 delta = n - m;
+        const u32 k0w = k0 + 16u;
+        const u32 a0 = k0w > delta ? (k0w - delta) >> 1 : 0u;
+        const uint64_t K = k0w > delta ? k0w - delta : 0u;
+        uint64_t x0l = rate ? ((30ull << 16) + rate - 1u) / rate : (uint64_t)m;
+        if (x0l > m) x0l = m;
+        const u32 x0 = (u32)x0l;
+        const uint64_t sr = ((uint64_t)rate * 3u) >> 2;                  // s * rate, per 2^16 rows
+        const uint64_t e_end = m > x0 ? (sr * (m - x0)) >> 16 : 0u;
+        a1 = K > e_end ? (u32)(((K - e_end) << 16) / ((2ull << 16) - sr)) : 0u;
+        if (a1 < 32u) a1 = 32u;
+        if (a0 + x0 + 64u >= m) a1 = a0;          // nothing left to narrow
+        const u32 packed = wedge_pack(a1, x0);
+        a1 = a1 + 16u >= a0 ? 0u : packed;      // a1 now holds the packed wedge request (0 = none)
+        if (a1 && k0w < kPadKFull) k0 = k0w;
+        if (wedge == 2) a1 = wedge_pack(32u, 0u); // test hook: narrow at once to the minimum, no cushion
+      }
     }
-    const BandGeom g = band_from_k(m ? m : 1u, n ? n : 1u, k0 >= kPadKFull ? 0xffffffffu : k0, !band);
+    const BandGeom g = band_from_k(m ? m : 1u, n ? n : 1u, k0 >= kPadKFull ? 0xffffffffu : k0, !band, a1);
     uint64_t key = ~0ull;
     int best = 0;
     // 32 candidates, one per lane: W in {2, 4, 8, 12, 16} x L in {1 .. 32}, + W in {20, 24} at L = 32
@@ -149,16 +192,17 @@ __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const Seq
     if (lane == 0) {
       const int shape = shape_id(best % kNumW, best / kNumW, hasn);
       pairs[p].pad = (k0 << 8) | (u32)shape;
+      pairs[p].aux = g.wedge() ? a1 : 0u;
       atomicAdd(&hist[shape], 1u);
     }
   }
 }
 
 cudaError_t launch_plan(PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, const uint2* planes, const u32* nplane,
-                        u32* hist, u32 lanes_total, int band, int force_shape, cudaStream_t stream) {
+                        u32* hist, u32 lanes_total, int band, int force_shape, int wedge, cudaStream_t stream) {
   if (n_pairs == 0) return cudaSuccess;
   const u32 blocks = std::min<u32>((n_pairs + 3) / 4, 148u * 16u);
-  plan_kernel<<<blocks, 128, 0, stream>>>(pairs, n_pairs, descs, planes, nplane, hist, lanes_total, band, force_shape);
+  plan_kernel<<<blocks, 128, 0, stream>>>(pairs, n_pairs, descs, planes, nplane, hist, lanes_total, band, force_shape, wedge);
   return cudaGetLastError();
 }
 

@@ -75,25 +75,56 @@ TRPA_HD int lmin_for(uint32_t n_pairs, uint32_t lanes) {
 // Banded kernel (myers3.cuh): geometry + cost model used to pick (W, L) per pair.
 // a = half band width below the main diagonal, ua = delta + a (above); see myers3.cuh.
 struct BandGeom {
-  uint32_t m, n, a, ua;
-  uint32_t k;   // effective threshold; 0xffffffff when the band covers the whole matrix
-  TRPA_HD uint32_t b0(uint32_t s, uint32_t R) const { const uint32_t x = s * R; return x > a ? (x - a) >> 5 : 0u; }
+  uint32_t m, n;
+  uint32_t a0, a1;      // half band width at the first / last pattern row (a1 < a0: wedge)
+  uint32_t row0;        // wedge: the band keeps its full width up to this pattern row
+  uint32_t taper_q;     // ((a0 - a1) << 20) / (m - row0)
+  uint32_t k;           // effective threshold; 0xffffffff when the band covers the whole matrix
+  TRPA_HD uint32_t a_at(uint32_t row) const {
+    if (!taper_q || row <= row0) return a0;
+    const uint32_t r = (row < m ? row : m) - row0;
+    return a0 - (uint32_t)(((uint64_t)r * taper_q) >> 20);
+  }
+  TRPA_HD uint32_t b0(uint32_t s, uint32_t R) const {
+    const uint32_t x = s * R, a = a_at(x);
+    return x > a ? (x - a) >> 5 : 0u;
+  }
   TRPA_HD uint32_t b1(uint32_t s, uint32_t R) const {
-    const uint32_t hi = (s + 1u) * R - 1u + ua;
+    const uint32_t hi = (s + 1u) * R - 1u + (n - m) + a_at(s * R);
     return (hi < n - 1u ? hi : n - 1u) >> 5;
   }
+  TRPA_HD bool wedge() const { return taper_q != 0; }
 };
 
 // threshold k -> band (m <= n).  The half width is at least 32 so that consecutive strips always
 // share a block; k = n is always sufficient (d <= n); patterns shorter than 64 are never banded.
-TRPA_HD BandGeom band_from_k(uint32_t m, uint32_t n, uint32_t k, bool force_full = false) {
+// wedge (0 = none) = a1 | (x0 / 64) << 20: requested half width a1 at the last row and the number of
+// rows x0 after the first a0 = (k - delta) / 2 ones for which the band keeps its full width; from row
+// a0 + x0 on it narrows linearly to a1 (a wedge is accepted only with the kernel's certificate).
+constexpr uint32_t kWedgeA1Bits = 20;
+TRPA_HD uint32_t wedge_pack(uint32_t a1, uint32_t x0) {
+  const uint32_t xq = (x0 + 63u) >> 6;
+  if (a1 >= (1u << kWedgeA1Bits) || xq >= (1u << (32 - kWedgeA1Bits))) return 0u;
+  return a1 | (xq << kWedgeA1Bits);
+}
+TRPA_HD BandGeom band_from_k(uint32_t m, uint32_t n, uint32_t k, bool force_full = false, uint32_t wedge = 0) {
   BandGeom g;
   const uint32_t delta = n - m;
-  g.m = m; g.n = n;
+  g.m = m; g.n = n; g.taper_q = 0; g.row0 = 0;
   if (k < delta + 64u) k = delta + 64u;
   if (k > n) k = n;
-  if (force_full || k < delta + 64u) { g.a = m; g.ua = n; g.k = 0xffffffffu; return g; }
-  g.a = (k - delta) >> 1; g.ua = delta + g.a; g.k = k;
+  if (force_full || k < delta + 64u) { g.a0 = g.a1 = m; g.k = 0xffffffffu; return g; }
+  g.a0 = g.a1 = (k - delta) >> 1; g.k = k;
+  if (wedge && m >= 256u) {
+    uint32_t a1 = wedge & ((1u << kWedgeA1Bits) - 1u);
+    const uint32_t row0 = g.a0 + ((wedge >> kWedgeA1Bits) << 6);
+    if (a1 < 32u) a1 = 32u;
+    if (a1 + 16u < g.a0 && row0 + 64u < m) {
+      g.a1 = a1; g.row0 = row0;
+      g.taper_q = (uint32_t)((((uint64_t)(g.a0 - a1)) << 20) / (m - row0));
+      if (!g.taper_q) { g.a1 = g.a0; g.row0 = 0; }
+    }
+  }
   return g;
 }
 

@@ -16,8 +16,11 @@ struct SeqDesc {
 };
 
 // One pairwise alignment request: getAlignment(A = descs[a], B = descs[b]) -> result slot `out`.
+// pad: distance hint on entry (0 = none); after planning bits 0..7 = kernel shape, bits 8..31 = band
+// threshold k0.  aux: after planning the wedge request (shapes.h wedge_pack: half width at the last
+// pattern row | rows of full width), 0 = the plain band.
 struct PairDesc {
-  uint32_t a, b, out, pad;
+  uint32_t a, b, out, pad, aux;
 };
 
 // One segment-staging request: cut [begin, begin+descs[desc].len) (0-based) out of sequence `seq`

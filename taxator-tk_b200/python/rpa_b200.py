@@ -27,7 +27,7 @@ class Profile(ctypes.Structure):
                 ("ms_stage", ctypes.c_double), ("launches_stage", ctypes.c_uint64), ("bytes_stage", ctypes.c_uint64),
                 ("ms_decide", ctypes.c_double), ("launches_decide", ctypes.c_uint64),
                 ("ms_other", ctypes.c_double), ("launches_other", ctypes.c_uint64),
-                ("rounds", ctypes.c_uint64), ("pairs", ctypes.c_uint64), ("band_retries", ctypes.c_uint64)]
+                ("rounds", ctypes.c_uint64), ("pairs", ctypes.c_uint64), ("band_retries", ctypes.c_uint64), ("wedge_failures", ctypes.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

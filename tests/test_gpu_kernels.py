@@ -158,7 +158,8 @@ def test_band_equals_full_matrix(ctx, with_n):
                 prof = ctx.profile()
                 assert np.array_equal(got, want), (lanes, k0, np.flatnonzero(got != want)[:10])
                 if k0 == 0:
-                    assert prof["band_retries"] == 0          # the planned threshold is a true upper bound
+                    # the planned threshold is a true upper bound: only a failed wedge certificate re-runs a pair
+                    assert prof["band_retries"] == prof["wedge_failures"]
                     assert prof["cells_edit_distance"] < cells_full
                 else:
                     assert prof["band_retries"] > 0
@@ -184,3 +185,63 @@ def test_band_long_pairs(ctx):
     finally:
         ctx.set_tuning("plan_lanes", 0)
         ctx.set_tuning("band_k0", 0)
+
+
+def _subst(rng, a, rates):
+    """substitutions only, rate per fifth of the sequence"""
+    b = np.frombuffer(a, np.uint8).copy()
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    n = len(b)
+    for q, r in enumerate(rates):
+        lo, hi = n * q // len(rates), n * (q + 1) // len(rates)
+        m = rng.random(hi - lo) < r
+        idx = np.searchsorted(alpha, b[lo:hi][m])
+        b[lo:hi][m] = alpha[(idx + rng.integers(1, 4, int(m.sum()))) % 4]
+    return b.tobytes()
+
+
+def test_wedge_is_exact_and_certified(ctx):
+    """The narrowing band (wedge) must give the oracle's integers whether its certificate holds
+    (uniform divergence) or fails and the pair is re-run (errors clustered at the end, an indel that
+    moves the alignment off the diagonal late); and it must execute fewer cells than the plain band."""
+    rng = np.random.default_rng(41)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    seqs, pa, pb = [], [], []
+    profiles = [[0.1] * 5, [0.2] * 5, [0.03] * 5, [0.0, 0.0, 0.0, 0.0, 0.6], [0.5, 0.0, 0.0, 0.0, 0.0], [0.02, 0.3, 0.02, 0.3, 0.02],
+                [0.15, 0.15, 0.0, 0.0, 0.0], [0.0, 0.0, 0.1, 0.2, 0.3]]
+    for t in range(240):
+        L = int(rng.choice([300, 1000, 2500, 5000, 9000]))
+        a = alpha[rng.integers(0, 4, L)].tobytes()
+        b = _subst(rng, a, profiles[t % len(profiles)])
+        if t % 6 == 5:      # one indel late in the sequence: Hamming stays small, the path leaves the diagonal
+            p = int(L * 0.9)
+            b = b[:p] + alpha[rng.integers(0, 4, int(rng.integers(1, 40)))].tobytes() + b[p:]
+        if t % 9 == 8:
+            p = int(L * 0.95)
+            b = b[:p] + b[p + int(rng.integers(1, 30)):]
+        seqs += [a, b]
+        pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)
+    chars, off, ln = _table(seqs)
+    want = np.array([_oracle_ed(seqs[a], seqs[b]) for a, b in zip(pa, pb)], np.int32)
+    try:
+        cells = {}
+        for wedge in (0, 1, 2):     # 2: the planner asks for the narrowest wedge at once (test hook)
+            for lanes in (0, 1 << 24):
+                ctx.set_tuning("wedge", wedge)
+                ctx.set_tuning("plan_lanes", lanes)
+                ctx.profile_reset()
+                got, _ = ctx.edit_distance_batch(chars, off, ln, pa, pb)
+                prof = ctx.profile()
+                assert np.array_equal(got, want), (wedge, lanes, np.flatnonzero(got != want)[:10])
+                cells[(wedge, lanes)] = prof["cells_edit_distance"]
+                if not wedge:
+                    assert prof["band_retries"] == 0 and prof["wedge_failures"] == 0
+                elif wedge == 1:
+                    assert prof["band_retries"] == prof["wedge_failures"] < len(pa) // 4
+                else:
+                    # far too narrow: most certificates fail, the pairs are re-run with the plain band
+                    assert prof["band_retries"] == prof["wedge_failures"] > len(pa) // 4
+        assert cells[(1, 1 << 24)] < cells[(0, 1 << 24)]   # the 5 kb / 9 kb pairs of 8+ % divergence qualify
+    finally:
+        ctx.set_tuning("wedge", 1)
+        ctx.set_tuning("plan_lanes", 0)

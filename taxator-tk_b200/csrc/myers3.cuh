@@ -14,7 +14,7 @@
 //  * schedule: a group of L lanes owns the pair; strip s runs on lane s % L in round r = s / L; at
 //    group step t it works on block t - T0(s), T0 = offset_r + (s % L), so a strip is always exactly
 //    one block behind the strip above it: lanes 1..L-1 take their top boundary (HP/HN shift-out
-//    bits, adder carries, running bottom-row value) from the lane above by shuffle; lane 0 takes it
+//    bits, running bottom-row value; the carry into a strip's adder IS the HN bit, see myers3_column) from the lane above by shuffle; lane 0 takes it
 //    from a per-group scratch line in L2 that lane L-1 wrote at least one step earlier (prefetched
 //    one step ahead).  offset_{r+1} - offset_r = L + gap_r with gap_r just large enough that no lane
 //    has to start a strip before it finished the previous one.
@@ -49,6 +49,35 @@ __device__ __forceinline__ void stcg_u4(uint4* p, uint4 v) {
 // PairDesc.pad as written by plan_kernel: bits 0..7 shape id, bits 8..31 initial threshold k0
 // (kPadKFull = no band).
 constexpr u32 kPadKFull = 0xffffffu;
+
+// One DP column for the W words of a lane (cf. myers2_column).  The carry into the strip's adder is the
+// HN bit handed down from the row above: the exact carry of the strip above only matters where
+// Eq = VN = 0 in bit 0, and there it equals that bit (Myers' block formulation: hin < 0 <=> Eq |= 1),
+// so no carry word travels between strips.
+template <int W>
+__device__ __forceinline__ void myers3_column(u32 (&VP)[W], u32 (&VN)[W], const u32 (&Eq)[W], u32 hpc, u32 hnc,
+                                              u32& hpOut, u32& hnOut) {
+  u32 T[W], S[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) T[w] = Eq[w] & VP[w];
+  add_words<W>(S, VP, T, hnc);
+  u32 hpPrev = hpc, hnPrev = hnc;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    const u32 X = Eq[w] | VN[w];
+    const u32 D0 = lop3<0xBE>(S[w], VP[w], X);       // (S ^ VP) | X
+    const u32 HN = VP[w] & D0;
+    const u32 HP = lop3<0xF1>(VN[w], VP[w], D0);     // VN | ~(VP | D0)
+    const u32 Xh = __funnelshift_l(hpPrev, HP, 1);
+    const u32 HNs = __funnelshift_l(hnPrev, HN, 1);
+    VN[w] = Xh & D0;
+    VP[w] = lop3<0xF1>(HNs, Xh, D0);                 // HNs | ~(Xh | D0)
+    hpPrev = HP;
+    hnPrev = HN;
+  }
+  hpOut = __funnelshift_l(hpPrev, hpOut, 1);
+  hnOut = __funnelshift_l(hnPrev, hnOut, 1);
+}
 
 // stats[0] += executed 32x32-cell word-blocks, stats[1] += band retries, stats[2] += pairs,
 // stats[3] += wedges whose certificate failed (re-run with the plain band)
@@ -89,7 +118,7 @@ myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __re
   u32 s = 0, r = 0, T0 = 0, sb0 = 0, sb1 = 0, pb1 = 0, nb0 = 0;
   int corner = 0, botacc = 0, tsum = 0, vfinal = 0, cert = 0x7fffffff;
   u32 VP[W], VN[W];
-  u32 hpOut = 0, hnOut = 0, cOut = 0;
+  u32 hpOut = 0, hnOut = 0;
   uint4 pre = make_uint4(0u, 0u, 0u, 0u);
   bool have_pre = false;
   u32 nblocks = 0, nretry = 0, npairs = 0, nwfail = 0;
@@ -103,7 +132,7 @@ myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __re
   auto start_attempt = [&]() {
     t = 0; s = sl; r = 0; T0 = sl;
     need_setup = s < S;
-    hpOut = 0; hnOut = 0; cOut = 0; botacc = 0;
+    hpOut = 0; hnOut = 0; botacc = 0;
     cert = 0x7fffffff;
   };
   auto setup_strip = [&]() {
@@ -185,11 +214,10 @@ myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __re
     const u32 src = sl == 0 ? lane : lane - 1;
     const u32 hpIn = __shfl_sync(0xffffffffu, hpOut, src);
     const u32 hnIn = __shfl_sync(0xffffffffu, hnOut, src);
-    const u32 cIn = __shfl_sync(0xffffffffu, cOut, src);
     const int botIn = __shfl_sync(0xffffffffu, botacc, src);
 
     bool do_block = false, islast = false, fin_lane = false;
-    u32 hpc = 0, hnc = 0, cc = 0, run = 32, b = 0;
+    u32 hpc = 0, hnc = 0, run = 32, b = 0;
     if (active && s < S) {
       if (need_setup) { setup_strip(); need_setup = false; }
       const int bi = (int)t - (int)T0;
@@ -200,9 +228,9 @@ myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __re
         if (s > 0 && b <= pb1) {  // the strip above computed this block
           if (sl == 0) {
             const uint4 q = have_pre ? pre : ldcg_u4(my_scratch + b);
-            hpc = q.x; hnc = q.y; cc = q.z; boti = (int)q.w;
-          } else { hpc = hpIn; hnc = hnIn; cc = cIn; boti = botIn; }
-        } else { hpc = 0xffffffffu; hnc = 0u; cc = 0u; }   // row 0, or upper bound (+1 deltas)
+            hpc = q.x; hnc = q.y; boti = (int)q.w;
+          } else { hpc = hpIn; hnc = hnIn; boti = botIn; }
+        } else { hpc = 0xffffffffu; hnc = 0u; }   // row 0, or upper bound (+1 deltas)
         if (b == sb0) {
           corner = s ? boti - (__popc(hpc) - __popc(hnc)) : 0;
           botacc = corner + (int)R;
@@ -223,7 +251,7 @@ myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __re
       const uint2 tx = planes[tw + b];
       u32 t0 = __brev(tx.x), t1 = __brev(tx.y), tN = 0;
       if (HASN) tN = __brev(nplane[tw + b]);
-      hpOut = 0; hnOut = 0; cOut = 0;
+      hpOut = 0; hnOut = 0;
       auto column = [&]() {
         u32 sym = (t0 >> 31) + 2u * (t1 >> 31);
         if (HASN) sym = (tN >> 31) ? (u32)(NSYM - 1) : sym;
@@ -237,8 +265,8 @@ myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __re
           if (4 * q + 2 < W) Eq[4 * q + 2] = e.z;
           if (4 * q + 3 < W) Eq[4 * q + 3] = e.w;
         }
-        myers2_column<W>(VP, VN, Eq, hpc, hnc, cc, hpOut, hnOut, cOut);
-        t0 <<= 1; t1 <<= 1; tN <<= 1; hpc <<= 1; hnc <<= 1; cc <<= 1;
+        myers3_column<W>(VP, VN, Eq, hpc, hnc, hpOut, hnOut);
+        t0 <<= 1; t1 <<= 1; tN <<= 1; hpc <<= 1; hnc <<= 1;
       };
       if (!any_partial) {
 #pragma unroll 4
@@ -252,7 +280,7 @@ myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __re
       }
       ++nblocks;
       botacc += __popc(hpOut) - __popc(hnOut);
-      if (sl == (u32)L - 1u && s + 1u < S) stcg_u4(my_scratch + b, make_uint4(hpOut, hnOut, cOut, (u32)botacc));
+      if (sl == (u32)L - 1u && s + 1u < S) stcg_u4(my_scratch + b, make_uint4(hpOut, hnOut, 0u, (u32)botacc));
       if (bg.wedge() && s + 1u < S) {   // certificate: cells through which a path can leave the region
         const int delta = (int)(n - m);
         if (b < nb0) cert = min(cert, botacc + (int)((s + 1u) * R - 32u * (b + 1u)) + delta);

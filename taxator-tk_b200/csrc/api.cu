@@ -151,6 +151,7 @@ struct trpa_ctx {
   DevBuf<PairDesc> d_pairs, d_pairs_sorted;
   DevBuf<StageReq> d_stage;
   DevBuf<uint2> arena_planes;
+  DevBuf<uint2> arena_codes;     // column codes of the staged words (common.cuh nt_codes)
   DevBuf<u32> arena_n;
   DevBuf<uint8_t> arena_aa;
   u64 arena_units = 0;
@@ -376,7 +377,7 @@ static int bucket_pairs3(trpa_ctx* c, Pipe& P, PairDesc* pairs, u32 n_pairs, con
 }
 
 static int launch_myers_shapes3(trpa_ctx* c, Pipe& P, const u32* h_hist, const PairDesc* sorted, const SeqDesc* descs,
-                                const uint2* planes, const u32* nplane, int* out, u32 max_len) {
+                                const uint2* planes, const u32* nplane, const uint2* codes, int* out, u32 max_len) {
   const u32 stride = (max_len + 31) / 32 + 1;
   CK(cudaMemsetAsync(P.d_hist.p + 2 * kNumShapes, 0, sizeof(u32) * kNumShapes, P.stream));
   // every shape bucket is one persistent launch; the buckets run concurrently (own stream, own
@@ -390,7 +391,7 @@ static int launch_myers_shapes3(trpa_ctx* c, Pipe& P, const u32* h_hist, const P
     const u32 cnt = h_hist[shape];
     if (!cnt) continue;
     u32 slots = 0;
-    CK(launch_myers3(shape, nullptr, cnt, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, &slots, P.stream));
+    CK(launch_myers3(shape, nullptr, cnt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, &slots, P.stream));
     jobs[nj++] = Job{shape, start, cnt, slots, scr_total};
     scr_total += (size_t)slots * stride;
     start += cnt;
@@ -425,7 +426,7 @@ static int launch_myers_shapes3(trpa_ctx* c, Pipe& P, const u32* h_hist, const P
       st = P.aux[a];
       if (a >= used) { CK(cudaStreamWaitEvent(st, P.fork_ev, 0)); used = a + 1; }
     }
-    CK(launch_myers3(jobs[j].shape, sorted + jobs[j].start, jobs[j].cnt, descs, planes, nplane, out,
+    CK(launch_myers3(jobs[j].shape, sorted + jobs[j].start, jobs[j].cnt, descs, planes, nplane, codes, out,
                      P.scratch3.p + jobs[j].scr, stride, P.d_hist.p + 2 * kNumShapes + jobs[j].shape, P.d_plan.p + 1,
                      c->band ? 0 : 1, nullptr, st));
     c->prof.launches_edit_distance++;
@@ -506,7 +507,7 @@ void trpa_destroy(trpa_ctx* c) {
   c->d_qd.release(); c->d_qsim.release(); c->d_bf_d.release(); c->d_cflags.release(); c->d_og_i.release(); c->d_tag.release();
   c->d_bf_node.release(); c->d_og_d.release(); c->d_res.release(); c->d_descs.release(); c->d_pairs.release();
   c->d_pairs_sorted.release(); c->d_stage.release();
-  c->arena_planes.release(); c->arena_n.release(); c->arena_aa.release();
+  c->arena_planes.release(); c->arena_codes.release(); c->arena_n.release(); c->arena_aa.release();
   for (int i = trpa_ctx::kMaxPipes - 1; i >= 0; --i) c->pipe[i].release();
   delete c;
 }
@@ -767,8 +768,8 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
     max_bound = std::max(max_bound, bound[s]);
     max_len = std::max(max_len, maxspan[s]);
   }
-  const u64 unit_bytes = protein ? 1 : 12;
-  const u64 have_units = protein ? (u64)c->arena_aa.cap : std::min<u64>(c->arena_planes.cap, c->arena_n.cap);
+  const u64 unit_bytes = protein ? 1 : 20;   // planes 8 + column codes 8 + N plane 4 per 32 bases
+  const u64 have_units = protein ? (u64)c->arena_aa.cap : std::min<u64>(std::min<u64>(c->arena_planes.cap, c->arena_codes.cap), c->arena_n.cap);
   u64 units_cap;
   if (!c->arena_bytes && have_units >= total_bound + 16) {
     units_cap = have_units - 16;   // the arena of an earlier batch is large enough: one chunk, no query
@@ -820,7 +821,7 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
       c->d_stage.ensure(nslots + 1))
     return TRPA_ERR_NOMEM;
   if (protein) { if (c->arena_aa.ensure(units_cap + 16)) return TRPA_ERR_NOMEM; }
-  else { if (c->arena_planes.ensure(units_cap + 2) || c->arena_n.ensure(units_cap + 2)) return TRPA_ERR_NOMEM; }
+  else { if (c->arena_planes.ensure(units_cap + 2) || c->arena_codes.ensure(units_cap + 2) || c->arena_n.ensure(units_cap + 2)) return TRPA_ERR_NOMEM; }
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   c->batch_ready = true;
@@ -885,9 +886,10 @@ static int step_pipe(trpa_ctx* c, Pipe& P, int pipe_index, size_t& next_chunk, c
     if (n_pairs == 0) {
       if (n_active) { set_error("internal: segments active without pending alignments"); return TRPA_ERR_STATE; }
       // algorithmic staging traffic of the chunk: packed store bits read + staged bits written
-      // (nt: 3 planes x 4 B per 32-base word each way; aa: 5 bit read + 1 byte written per residue)
+      // (nt: 3 planes x 4 B per 32-base word read, those + 8 B of column codes written; aa: 5 bit read +
+      // 1 byte written per residue)
       const u64 units = P.h_counters[CN_ARENA];
-      c->prof.bytes_stage += protein ? (units * 13) / 8 : units * 24;
+      c->prof.bytes_stage += protein ? (units * 13) / 8 : units * 32;
       if (!protein && v3) { const int rc = harvest_band_stats(c, P); if (rc) return rc; }
       return start_chunk(c, P, pipe_index, next_chunk, base);
     }
@@ -900,7 +902,7 @@ static int step_pipe(trpa_ctx* c, Pipe& P, int pipe_index, size_t& next_chunk, c
       CK(launch_stage_aa(P.B.stage, n_stage, Q.packed.p, Q.woff.p, R.packed.p, R.woff.p, c->d_descs.p, c->arena_aa.p, P.stream));
     else
       CK(launch_stage_nt(P.B.stage, n_stage, Q.planes.p, Q.nplane.p, Q.woff.p, R.planes.p, R.nplane.p, R.woff.p,
-                         c->d_descs.p, c->arena_planes.p, c->arena_n.p, P.stream));
+                         c->d_descs.p, c->arena_planes.p, c->arena_n.p, c->arena_codes.p, P.stream));
     end_event(P, ev);
     if (n_stage) c->prof.launches_stage++;
     if (protein) {
@@ -933,7 +935,7 @@ static int step_pipe(trpa_ctx* c, Pipe& P, int pipe_index, size_t& next_chunk, c
     // --- align: one persistent launch per non-empty shape
     const u32* h_hist = P.h_counters + kNumCounters;
     const int ev = begin_event(P, EV_MYERS);
-    const int rc = v3 ? launch_myers_shapes3(c, P, h_hist, P.sorted, c->d_descs.p, c->arena_planes.p, c->arena_n.p,
+    const int rc = v3 ? launch_myers_shapes3(c, P, h_hist, P.sorted, c->d_descs.p, c->arena_planes.p, c->arena_n.p, c->arena_codes.p,
                                              c->d_res.p, c->max_stage_len)
                       : launch_myers_shapes(c, P, h_hist, P.sorted, c->d_descs.p, c->arena_planes.p, c->arena_n.p,
                                             c->d_res.p, c->max_stage_len);
@@ -1053,9 +1055,9 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   u64 words = 0; u32 max_len = 0;
   for (u32 i = 0; i < n_seq; ++i) { sd[i] = SeqDesc{(u32)words, len[i], 0, 0}; words += ((u64)len[i] + 31) / 32; max_len = std::max(max_len, len[i]); }
   if (words >= 0xffffffffull) { set_error("table too large"); return TRPA_ERR_ARG; }
-  DevBuf<SeqDesc> d_sd; DevBuf<uint2> planes; DevBuf<u32> nplane; DevBuf<PairDesc> d_pairs, d_sorted; DevBuf<int32_t> d_out;
+  DevBuf<SeqDesc> d_sd; DevBuf<uint2> planes, codes; DevBuf<u32> nplane; DevBuf<PairDesc> d_pairs, d_sorted; DevBuf<int32_t> d_out;
   DevBuf<u32> d_cnt;
-  if (d_sd.ensure(n_seq + 1) || planes.ensure(words + 2) || nplane.ensure(words + 2) || d_pairs.ensure(n_pairs) ||
+  if (d_sd.ensure(n_seq + 1) || planes.ensure(words + 2) || codes.ensure(words + 2) || nplane.ensure(words + 2) || d_pairs.ensure(n_pairs) ||
       d_sorted.ensure(n_pairs) || d_out.ensure(n_pairs) || d_cnt.ensure(kNumCounters))
     return TRPA_ERR_NOMEM;
   CK(cudaMemcpyAsync(d_sd.p, sd.data(), sizeof(SeqDesc) * n_seq, cudaMemcpyHostToDevice, c->stream));
@@ -1066,6 +1068,7 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   if (d_flags.ensure(n_seq + 1)) return TRPA_ERR_NOMEM;
   CK(cudaMemsetAsync(d_flags.p, 0, sizeof(u32) * (n_seq + 1), c->stream));
   CK(launch_pack_nt(d_chars.p, d_off.p, d_sd.p, n_seq, words, planes.p, nplane.p, d_flags.p, c->stream));
+  CK(launch_codes_from_planes(planes.p, codes.p, words + 2, c->stream));
   std::vector<u32> h_flags(n_seq);
   CK(cudaMemcpyAsync(h_flags.data(), d_flags.p, sizeof(u32) * n_seq, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -1087,13 +1090,13 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   if (repeat < 1) repeat = 1;
   // one untimed pass when timing is requested
   if (kernel_ms && repeat > 1) {
-    rc = v3 ? launch_myers_shapes3(c, P, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len)
+    rc = v3 ? launch_myers_shapes3(c, P, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, codes.p, d_out.p, max_len)
             : launch_myers_shapes(c, P, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
     if (rc) return rc;
   }
   CK(cudaEventRecord(e0, c->stream));
   for (int r = 0; r < repeat; ++r) {
-    rc = v3 ? launch_myers_shapes3(c, P, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len)
+    rc = v3 ? launch_myers_shapes3(c, P, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, codes.p, d_out.p, max_len)
             : launch_myers_shapes(c, P, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
     if (rc) return rc;
   }
@@ -1105,7 +1108,7 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   if (kernel_ms) *kernel_ms = ms / repeat;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (v3) { rc = harvest_band_stats(c, P); if (rc) return rc; }
-  d_chars.release(); d_off.release(); d_sd.release(); planes.release(); nplane.release(); d_pairs.release();
+  d_chars.release(); d_off.release(); d_sd.release(); planes.release(); codes.release(); nplane.release(); d_pairs.release();
   d_sorted.release(); d_out.release(); d_cnt.release(); d_flags.release();
   return 0;
 }
@@ -1213,7 +1216,7 @@ int trpa_fetch_segments(trpa_ctx* c, const uint32_t* ref_seq, const uint32_t* st
   } else {
     DevBuf<uint2> pl; DevBuf<u32> pn;
     if (pl.ensure(units + 2) || pn.ensure(units + 2)) return TRPA_ERR_NOMEM;
-    CK(launch_stage_nt(d_rq.p, n, nullptr, nullptr, nullptr, R.planes.p, R.nplane.p, R.woff.p, d_sd.p, pl.p, pn.p, c->stream));
+    CK(launch_stage_nt(d_rq.p, n, nullptr, nullptr, nullptr, R.planes.p, R.nplane.p, R.woff.p, d_sd.p, pl.p, pn.p, nullptr, c->stream));
     CK(launch_unstage_nt(d_sd.p, n, pl.p, pn.p, d_ooff.p, d_out.p, c->stream));
     CK(cudaMemcpyAsync(out_codes, d_out.p, total, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

@@ -20,7 +20,7 @@ cudaError_t launch_plan(PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, cons
 // pairs[0..count) all of `shape`; scratch: scratch_stride uint4 per group slot (slots_out != nullptr:
 // only report how many slots the launch would use); stats: {word-blocks, retries, pairs, failed wedges} accumulators
 cudaError_t launch_myers3(int shape, const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint2* planes,
-                          const u32* nplane, int* out, uint4* scratch, u32 scratch_stride, u32* cursor,
+                          const u32* nplane, const uint2* codes, int* out, uint4* scratch, u32 scratch_stride, u32* cursor,
                           unsigned long long* stats, int force_full, u32* slots_out, cudaStream_t stream);
 
 // BLOSUM62 linear-gap NW with traced length; out2[pair.out] = {mutual, #diagonal steps}
@@ -38,7 +38,8 @@ cudaError_t launch_pack_aa(const uint8_t* chars, const u64* off, const u64* woff
                            u64 total_words, u32* packed, cudaStream_t stream);
 cudaError_t launch_stage_nt(const StageReq* reqs, u32 n_req, const uint2* q_planes, const u32* q_n, const u64* q_woff,
                             const uint2* r_planes, const u32* r_n, const u64* r_woff, SeqDesc* descs,
-                            uint2* out_planes, u32* out_n, cudaStream_t stream);
+                            uint2* out_planes, u32* out_n, uint2* out_codes, cudaStream_t stream);
+cudaError_t launch_codes_from_planes(const uint2* planes, uint2* codes, u64 n_words, cudaStream_t stream);
 cudaError_t launch_stage_aa(const StageReq* reqs, u32 n_req, const u32* q_packed, const u64* q_woff,
                             const u32* r_packed, const u64* r_woff, SeqDesc* descs, uint8_t* out, cudaStream_t stream);
 cudaError_t launch_selfscore(SeqDesc* descs, u32 n, const uint8_t* residues, cudaStream_t stream);

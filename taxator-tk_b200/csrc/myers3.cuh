@@ -50,6 +50,31 @@ __device__ __forceinline__ void stcg_u4(uint4* p, uint4 v) {
 // (kPadKFull = no band).
 constexpr u32 kPadKFull = 0xffffffu;
 
+// Equality-mask table in shared memory: entry(sym, wq) of a lane = the masks of pattern words 4wq..4wq+3 of
+// its strip for text symbol sym (one uint4; the 32 lanes of a warp are contiguous: conflict-free LDS.128).
+//  * pairs without N: the table of a warp is 2 KB aligned and laid out [wq][sym][lane], so the address of a
+//    column's row is ONE LOP3 -- base | (codes >> shift) & 0x600 -- on the text's 2-bit column codes
+//    (common.cuh nt_codes, written by the staging kernel) and wq is an immediate offset of the load;
+//  * pairs with N (5 symbols, rare): [sym][wq][lane], symbol taken from the three bit-planes.
+template <int W, bool HASN>
+struct Myers3Cfg {
+  static constexpr int WQ = (W + 3) / 4;
+  static constexpr int NSYM = HASN ? 5 : 4;
+  static constexpr int kWarps = 4;
+  static constexpr u32 kWarpBytes = HASN ? (u32)(NSYM * WQ * 512) : (u32)(WQ * 2048);
+  static constexpr size_t kSmemBytes = (size_t)kWarps * kWarpBytes + (HASN ? 0 : 2048);
+  __device__ static constexpr u32 entry(int sym, int wq) { return HASN ? (u32)((sym * WQ + wq) * 512) : (u32)(wq * 2048 + sym * 512); }
+};
+
+__device__ __forceinline__ uint4 lds_u4(u32 addr, u32 imm) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr + imm));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(u32 addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // One DP column for the W words of a lane (cf. myers2_column).  The carry into the strip's adder is the
 // HN bit handed down from the row above: the exact carry of the strip above only matters where
 // Eq = VN = 0 in bit 0, and there it equals that bit (Myers' block formulation: hin < 0 <=> Eq |= 1),
@@ -84,10 +109,11 @@ __device__ __forceinline__ void myers3_column(u32 (&VP)[W], u32 (&VN)[W], const 
 template <int W, bool HASN>
 __global__ void __launch_bounds__(128)
 myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __restrict__ seqs,
-              const uint2* __restrict__ planes, const u32* __restrict__ nplane, int* __restrict__ out, int L,
-              uint4* __restrict__ scratch, u32 scratch_stride, const uint2* __restrict__ bucket,
-              u32* __restrict__ cursor, unsigned long long* __restrict__ stats, int force_full) {
-  typedef Myers2Cfg<W, HASN> Cfg;
+              const uint2* __restrict__ planes, const u32* __restrict__ nplane, const uint2* __restrict__ codes,
+              int* __restrict__ out, int L, uint4* __restrict__ scratch, u32 scratch_stride,
+              const uint2* __restrict__ bucket, u32* __restrict__ cursor, unsigned long long* __restrict__ stats,
+              int force_full) {
+  typedef Myers3Cfg<W, HASN> Cfg;
   constexpr int WQ = Cfg::WQ;
   constexpr int NSYM = Cfg::NSYM;
   constexpr u32 R = 32u * W;
@@ -106,7 +132,9 @@ myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __re
   const u32 gmask = (L == 32 ? 0xffffffffu : ((1u << L) - 1u) << (g * L));
   const u32 warp_gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 slot = warp_gid * G + g;
-  uint4* my = eqtab + (size_t)warp_in_cta * NSYM * WQ * 32 + lane;   // entry(sym, wq) = my[(sym*WQ + wq)*32]
+  u32 sbase = (u32)__cvta_generic_to_shared(eqtab);
+  if (!HASN) sbase = (sbase + 2047u) & ~2047u;
+  const u32 mybase = sbase + warp_in_cta * Cfg::kWarpBytes + lane * 16u;   // + Cfg::entry(sym, wq)
   uint4* my_scratch = scratch + (size_t)slot * scratch_stride;
 
   bool active = false, exhausted = !in_group, need_setup = false;
@@ -164,7 +192,7 @@ myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __re
         if (HASN) e[NSYM - 1][j] = pn; // N matches N
       }
 #pragma unroll
-      for (int sym = 0; sym < NSYM; ++sym) my[(sym * WQ + q) * 32] = make_uint4(e[sym][0], e[sym][1], e[sym][2], e[sym][3]);
+      for (int sym = 0; sym < NSYM; ++sym) sts_u4(mybase + Cfg::entry(sym, q), make_uint4(e[sym][0], e[sym][1], e[sym][2], e[sym][3]));
     }
 #pragma unroll
     for (int w = 0; w < W; ++w) { VP[w] = 0xffffffffu; VN[w] = 0u; }
@@ -248,35 +276,55 @@ myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __re
     }
     const bool any_partial = __any_sync(0xffffffffu, do_block && run < 32u);
     if (do_block) {
-      const uint2 tx = planes[tw + b];
-      u32 t0 = __brev(tx.x), t1 = __brev(tx.y), tN = 0;
-      if (HASN) tN = __brev(nplane[tw + b]);
       hpOut = 0; hnOut = 0;
-      auto column = [&]() {
-        u32 sym = (t0 >> 31) + 2u * (t1 >> 31);
-        if (HASN) sym = (tN >> 31) ? (u32)(NSYM - 1) : sym;
-        const uint4* row = my + sym * (WQ * 32);
+      // one column: row = shared address of the lane's entry (sym, 0) for the column's text symbol
+      auto column = [&](u32 row) {
         u32 Eq[W];
 #pragma unroll
         for (int q = 0; q < WQ; ++q) {
-          const uint4 e = row[q * 32];
+          const uint4 e = lds_u4(row, Cfg::entry(0, q));
           if (4 * q + 0 < W) Eq[4 * q + 0] = e.x;
           if (4 * q + 1 < W) Eq[4 * q + 1] = e.y;
           if (4 * q + 2 < W) Eq[4 * q + 2] = e.z;
           if (4 * q + 3 < W) Eq[4 * q + 3] = e.w;
         }
         myers3_column<W>(VP, VN, Eq, hpc, hnc, hpOut, hnOut);
-        t0 <<= 1; t1 <<= 1; tN <<= 1; hpc <<= 1; hnc <<= 1;
+        hpc <<= 1; hnc <<= 1;
       };
-      if (!any_partial) {
-#pragma unroll 4
-        for (int c = 0; c < 32; ++c) column();
-      } else {
-        // some lane of the warp is in the partial final block of its last strip: everybody takes the
-        // per-column predicated loop for this one step instead of serialising two loops
+      if (!HASN) {
+        const uint2 cx = codes[tw + b];   // 2-bit column codes, first column in the low bits
+        if (!any_partial) {
+          u32 x = cx.x;
 #pragma unroll 1
-        for (u32 c = 0; c < 32u; ++c)
-          if (c < run) column();
+          for (int g4 = 0; g4 < 8; ++g4) {
+            if (g4 == 4) x = cx.y;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) column(lop3<0xF8>(mybase, x << (9 - 2 * j), 0x600u));   // base | sym << 9
+            x >>= 8;
+          }
+        } else {
+          // some lane of the warp is in the partial final block of its last strip: everybody takes the
+          // per-column predicated loop for this one step instead of serialising two loops
+#pragma unroll 1
+          for (u32 c = 0; c < 32u; ++c)
+            if (c < run) column(mybase + ((((c < 16u ? cx.x : cx.y) >> (2u * (c & 15u))) & 3u) << 9));
+        }
+      } else {
+        const uint2 tx = planes[tw + b];
+        u32 t0 = __brev(tx.x), t1 = __brev(tx.y), tN = __brev(nplane[tw + b]);
+        auto column_n = [&]() {
+          const u32 sym = (tN >> 31) ? (u32)(NSYM - 1) : (t0 >> 31) + 2u * (t1 >> 31);
+          column(mybase + sym * Cfg::entry(1, 0));
+          t0 <<= 1; t1 <<= 1; tN <<= 1;
+        };
+        if (!any_partial) {
+#pragma unroll 4
+          for (int c = 0; c < 32; ++c) column_n();
+        } else {
+#pragma unroll 1
+          for (u32 c = 0; c < 32u; ++c)
+            if (c < run) column_n();
+        }
       }
       ++nblocks;
       botacc += __popc(hpOut) - __popc(hnOut);

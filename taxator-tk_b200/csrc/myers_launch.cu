@@ -208,10 +208,10 @@ cudaError_t launch_plan(PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, cons
 
 template <int W, bool HASN>
 static cudaError_t launch_one3(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint2* planes,
-                               const u32* nplane, int* out, int L, uint4* scratch, u32 scratch_stride,
+                               const u32* nplane, const uint2* codes, int* out, int L, uint4* scratch, u32 scratch_stride,
                                u32* cursor, unsigned long long* stats, int force_full, u32* slots_out,
                                cudaStream_t stream) {
-  typedef Myers2Cfg<W, HASN> Cfg;
+  typedef Myers3Cfg<W, HASN> Cfg;
   static int occ = 0;
   if (occ == 0) {
     cudaError_t e = cudaFuncSetAttribute(myers3_kernel<W, HASN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
@@ -232,30 +232,30 @@ static cudaError_t launch_one3(const PairDesc* pairs, u32 count, const SeqDesc* 
   const u32 resident = (u32)g_num_sms * (u32)occ;
   if (blocks > resident) blocks = resident;
   if (slots_out) { *slots_out = blocks * 4 * G; return cudaSuccess; }
-  myers3_kernel<W, HASN><<<blocks, 128, Cfg::kSmemBytes, stream>>>(pairs, count, seqs, planes, nplane, out, L, scratch,
+  myers3_kernel<W, HASN><<<blocks, 128, Cfg::kSmemBytes, stream>>>(pairs, count, seqs, planes, nplane, codes, out, L, scratch,
                                                                   scratch_stride, nullptr, cursor, stats, force_full);
   return cudaGetLastError();
 }
 
 // slots_out != nullptr: only report the number of group slots (scratch lines) the launch would use
 cudaError_t launch_myers3(int shape, const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint2* planes,
-                          const u32* nplane, int* out, uint4* scratch, u32 scratch_stride, u32* cursor,
+                          const u32* nplane, const uint2* codes, int* out, uint4* scratch, u32 scratch_stride, u32* cursor,
                           unsigned long long* stats, int force_full, u32* slots_out, cudaStream_t stream) {
   if (count == 0) { if (slots_out) *slots_out = 0; return cudaSuccess; }
   const int L = 1 << shape_lidx(shape);
   const bool hasn = shape_hasn(shape) != 0;
 #define TRPA_CASE3(I, WV)                                                                                          \
   case I:                                                                                                          \
-    return hasn ? launch_one3<WV, true>(pairs, count, seqs, planes, nplane, out, L, scratch, scratch_stride, cursor, \
+    return hasn ? launch_one3<WV, true>(pairs, count, seqs, planes, nplane, codes, out, L, scratch, scratch_stride, cursor, \
                                         stats, force_full, slots_out, stream)                                      \
-                : launch_one3<WV, false>(pairs, count, seqs, planes, nplane, out, L, scratch, scratch_stride, cursor, \
+                : launch_one3<WV, false>(pairs, count, seqs, planes, nplane, codes, out, L, scratch, scratch_stride, cursor, \
                                          stats, force_full, slots_out, stream);
   switch (shape_widx(shape)) {
     TRPA_CASE3(0, 1) TRPA_CASE3(1, 2) TRPA_CASE3(2, 4) TRPA_CASE3(3, 8) TRPA_CASE3(4, 12) TRPA_CASE3(5, 16) TRPA_CASE3(6, 20)
     default:
-      return hasn ? launch_one3<24, true>(pairs, count, seqs, planes, nplane, out, L, scratch, scratch_stride, cursor,
+      return hasn ? launch_one3<24, true>(pairs, count, seqs, planes, nplane, codes, out, L, scratch, scratch_stride, cursor,
                                           stats, force_full, slots_out, stream)
-                  : launch_one3<24, false>(pairs, count, seqs, planes, nplane, out, L, scratch, scratch_stride, cursor,
+                  : launch_one3<24, false>(pairs, count, seqs, planes, nplane, codes, out, L, scratch, scratch_stride, cursor,
                                            stats, force_full, slots_out, stream);
   }
 #undef TRPA_CASE3

@@ -86,6 +86,24 @@ cudaError_t launch_pack_nt(const uint8_t* chars, const u64* off, const SeqDesc* 
   return cudaGetLastError();
 }
 
+// column codes (common.cuh nt_codes) for a whole plane array (low-level pair API; the batch path gets
+// them from the staging kernel)
+__global__ void codes_from_planes_kernel(const uint2* __restrict__ planes, uint2* __restrict__ codes, u64 n_words) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+    const uint2 p = planes[w];
+    codes[w] = nt_codes(p.x, p.y);
+  }
+}
+
+cudaError_t launch_codes_from_planes(const uint2* planes, uint2* codes, u64 n_words, cudaStream_t stream) {
+  if (n_words == 0) return cudaSuccess;
+  u64 blocks = (n_words + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  codes_from_planes_kernel<<<(u32)blocks, 256, 0, stream>>>(planes, codes, n_words);
+  return cudaGetLastError();
+}
+
 // ASCII -> one ordinal byte per residue at the same offsets
 __global__ void aa_codes_kernel(const uint8_t* __restrict__ chars, uint8_t* __restrict__ out, u64 n) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
@@ -152,7 +170,8 @@ __device__ __forceinline__ u32 window_n(const u32* p, long long s) {
 __global__ void stage_nt_kernel(const StageReq* __restrict__ reqs, u32 n_req,
                                 const uint2* __restrict__ q_planes, const u32* __restrict__ q_n, const u64* __restrict__ q_woff,
                                 const uint2* __restrict__ r_planes, const u32* __restrict__ r_n, const u64* __restrict__ r_woff,
-                                SeqDesc* __restrict__ descs, uint2* __restrict__ out_planes, u32* __restrict__ out_n) {
+                                SeqDesc* __restrict__ descs, uint2* __restrict__ out_planes, u32* __restrict__ out_n,
+                                uint2* __restrict__ out_codes) {
   const u32 lane = threadIdx.x & 31;
   const u32 warps = (gridDim.x * blockDim.x) >> 5;
   for (u32 r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_req; r += warps) {
@@ -178,6 +197,7 @@ __global__ void stage_nt_kernel(const StageReq* __restrict__ reqs, u32 n_req,
       p0 &= valid & ~pn; p1 &= valid & ~pn;
       out_planes[(u64)d.woff + k] = make_uint2(p0, p1);
       out_n[(u64)d.woff + k] = pn;
+      if (out_codes) out_codes[(u64)d.woff + k] = nt_codes(p0, p1);
       anyn |= pn;
     }
     anyn = __reduce_or_sync(0xffffffffu, anyn);
@@ -187,12 +207,12 @@ __global__ void stage_nt_kernel(const StageReq* __restrict__ reqs, u32 n_req,
 
 cudaError_t launch_stage_nt(const StageReq* reqs, u32 n_req, const uint2* q_planes, const u32* q_n, const u64* q_woff,
                             const uint2* r_planes, const u32* r_n, const u64* r_woff, SeqDesc* descs,
-                            uint2* out_planes, u32* out_n, cudaStream_t stream) {
+                            uint2* out_planes, u32* out_n, uint2* out_codes, cudaStream_t stream) {
   if (n_req == 0) return cudaSuccess;
   u32 blocks = (n_req + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
   stage_nt_kernel<<<blocks, 256, 0, stream>>>(reqs, n_req, q_planes, q_n, q_woff, r_planes, r_n, r_woff, descs,
-                                              out_planes, out_n);
+                                              out_planes, out_n, out_codes);
   return cudaGetLastError();
 }
 

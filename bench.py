@@ -345,8 +345,14 @@ def main():
     # the algorithmic rate (cells of the reference's full matrices / time) is given beside it.
     executed_cells = float(prof["cells_edit_distance"]) if not fd.protein else cells_step * args.steps
     achieved = executed_cells / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
+    try:
+        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        ncu_traffic = {}
+    tr = ncu_traffic.get(kname, {})
     roofline = {"bound": "int32_alu", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GCUPS",
-                "frac": achieved / peak if peak else None, "traffic": None,
+                "frac": achieved / peak if peak else None, "traffic": tr.get("bytes_per_launch"),
+                "traffic_source": tr.get("source"),
                 "achieved_algorithmic": algorithmic,
                 "executed_cell_fraction": executed_cells / (cells_step * args.steps) if cells_step else None,
                 "band": bool(args.band) and not fd.protein, "band_retries_per_step": prof["band_retries"] / args.steps,
@@ -362,10 +368,12 @@ def main():
     roofline_hbm = None
     if prof["ms_stage"] > 0:
         # algorithmic bytes of staging: packed store bits read + staged bits written
-        # (nt: 3 planes x 4 B per 32-base word each way; aa: 5 bit read + 1 byte written per residue)
+        # (nt: 3 planes x 4 B per 32-base word read, those + 8 B of column codes written; aa: 5 bit read +
+        # 1 byte written per residue)
         gbs = prof["bytes_stage"] / (prof["ms_stage"] / 1e3) / 1e9
         roofline_hbm = {"bound": "hbm", "kernel": "stage_kernel", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": gbs / hbm_peak, "traffic": None,
+                        "frac": gbs / hbm_peak, "traffic": ncu_traffic.get("stage_kernel", {}).get("bytes_per_launch") if not fd.protein else None,
+                        "traffic_source": ncu_traffic.get("stage_kernel", {}).get("source") if not fd.protein else None,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                         "bytes_per_step": prof["bytes_stage"] / args.steps,
                         "ms_per_step": prof["ms_stage"] / args.steps}

@@ -166,6 +166,7 @@ struct trpa_ctx {
   u32 la_cap = 300000;        // pairs per round the automatic look-ahead aims for (measured: C2 +10 %, C1 2.4x vs none)
   u32 la_max = 32;            // largest automatic look-ahead budget per segment and round
   int force_shape = -1;       // tuning hook: (lidx * kNumW + widx) forced for every pair, -1 = planner
+  PlanParams plan;            // hint margin + cost model of the shape planner (tuning hooks)
   u32 plan_lanes = 0;         // test hook: lanes the shape planner assumes (0 = num_sms * 16 warps * 32)
   int num_sms = 148;
   // profiling
@@ -368,7 +369,7 @@ static int bucket_pairs3(trpa_ctx* c, Pipe& P, PairDesc* pairs, u32 n_pairs, con
   CK(cudaMemsetAsync(P.d_hist.p, 0, sizeof(u32) * 3 * kNumShapes, P.stream));
   const u32 blocks = std::min<u32>((n_pairs + 255) / 256, 148 * 8);
   CK(launch_plan(pairs, n_pairs, descs, planes, nplane, P.d_hist.p, c->plan_lanes ? c->plan_lanes : (u32)c->num_sms * 16u * 32u,
-                 c->band ? (c->band_k0 ? (int)c->band_k0 : 1) : 0, c->force_shape, c->wedge, P.stream));
+                 c->band ? (c->band_k0 ? (int)c->band_k0 : 1) : 0, c->force_shape, c->wedge, c->plan, P.stream));
   scan_kernel<<<1, 32, 0, P.stream>>>(P.d_hist.p, P.d_buckets.p);
   scatter_kernel<<<blocks, 256, 0, P.stream>>>(pairs, n_pairs, P.d_hist.p, sorted);
   CK(cudaGetLastError());
@@ -536,6 +537,13 @@ int trpa_set_tuning(trpa_ctx* c, const char* key, int64_t value) {
   if (!c || !key) { set_error("bad arguments"); return TRPA_ERR_ARG; }
   const std::string k(key);
   if (k == "band_k0") c->band_k0 = value < 0 ? 0u : (u32)std::min<int64_t>(value, 0xfffffe);
+  else if (k == "hint_mul64") c->plan.hint_mul64 = (u32)std::max<int64_t>(1, std::min<int64_t>(value, 1 << 16));
+  else if (k == "hint_add") c->plan.hint_add = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
+  else if (k == "cost_word10") c->plan.word10 = (u32)std::max<int64_t>(1, std::min<int64_t>(value, 1 << 16));
+  else if (k == "cost_col10") c->plan.col10 = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 16));
+  else if (k == "cost_step") c->plan.step = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
+  else if (k == "cost_setup") c->plan.setup = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
+  else if (k == "cost_setup_w") c->plan.setup_w = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 16));
   else if (k == "plan_lanes") c->plan_lanes = value < 0 ? 0u : (u32)std::min<int64_t>(value, 1 << 30);
   else if (k == "myers_version") c->myers_version = value == 2 ? 2 : 3;
   else if (k == "wedge") c->wedge = value < 0 ? 0 : (value > 2 ? 2 : (int)value);   // 2: test hook, see plan_kernel

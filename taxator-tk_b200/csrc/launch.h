@@ -1,6 +1,7 @@
 // Host-side launch entry points of the CUDA translation units.
 #pragma once
 #include "common.cuh"
+#include "shapes.h"
 
 namespace trpa {
 
@@ -16,7 +17,7 @@ u32 myers_group_slots(int shape, u32 count);
 // round (PairDesc.pad: hint on entry; bits 0..7 shape, 8..31 k0 on exit) and the per-shape histogram.
 // band: 0 = full matrix, 1 = band, > 1 = band with that forced initial threshold (test hook).
 cudaError_t launch_plan(PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, const uint2* planes, const u32* nplane,
-                        u32* hist, u32 lanes_total, int band, int force_shape, int wedge, cudaStream_t stream);
+                        u32* hist, u32 lanes_total, int band, int force_shape, int wedge, const PlanParams& pp, cudaStream_t stream);
 // pairs[0..count) all of `shape`; scratch: scratch_stride uint4 per group slot (slots_out != nullptr:
 // only report how many slots the launch would use); stats: {word-blocks, retries, pairs, failed wedges} accumulators
 cudaError_t launch_myers3(int shape, const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint2* planes,

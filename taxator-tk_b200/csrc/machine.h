@@ -173,13 +173,17 @@ struct Machine {
     const uint64_t e = (uint64_t)(r.alnlen - r.identities) * S.qrlength / r.alnlen;
     return (uint32_t)(e < 0x7fffffffu ? e + 1u : 0x7fffffffu);
   }
-  // segment i <-> segment j: triangle inequality over the query, exact query distances where known
+  // segment i <-> segment j: triangle inequality over the query, exact query distances where known.
+  // Bit 31 (kHintIsBound): both query distances are exact edit distances of the very strings the pair
+  // aligns, so the sum is a true upper bound and the planner adds no safety margin.
   TRPA_HD uint32_t hint_pair(uint32_t i, uint32_t j) const {
     if (B.protein) return 0u;
-    const float di = qd[i] != FLT_MAX && (fl[i] & CF_P0_ALIGNED) ? qd[i] : (float)hint_query(i);
-    const float dj = qd[j] != FLT_MAX && (fl[j] & CF_P0_ALIGNED) ? qd[j] : (float)hint_query(j);
+    const bool xi = qd[i] != FLT_MAX && (fl[i] & CF_P0_ALIGNED), xj = qd[j] != FLT_MAX && (fl[j] & CF_P0_ALIGNED);
+    const float di = xi ? qd[i] : (float)hint_query(i);
+    const float dj = xj ? qd[j] : (float)hint_query(j);
     const float e = di + dj;
-    return e < 2.0e9f ? (uint32_t)e + 1u : 0x7fffffffu;
+    if (!(e < 1.0e9f)) return 0x7fffffffu;
+    return ((uint32_t)e + 1u) | (xi && xj ? kHintIsBound : 0u);
   }
   // cells are counted when an alignment is consumed, i.e. exactly for the alignments the reference
   // performs; look-ahead results that are never consumed do not count

@@ -93,7 +93,7 @@ cudaError_t launch_myers(int shape, const PairDesc* pairs, u32 count, const SeqD
 // when pairs are plentiful, latency when they are scarce).  pad <- shape | k0 << 8; histogram.
 __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const SeqDesc* __restrict__ descs,
                             const uint2* __restrict__ planes, const u32* __restrict__ nplane,
-                            u32* __restrict__ hist, u32 lanes_total, int band, int force_shape, int wedge) {
+                            u32* __restrict__ hist, u32 lanes_total, int band, int force_shape, int wedge, const PlanParams pp) {
   const u32 lane = threadIdx.x & 31;
   const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -129,7 +129,9 @@ __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const Seq
       const u32 hint = pd.pad;
       bool from_hint = false;
       if (hint) {
-        const u32 hk = hint + (hint >> 3) + 32u;  // estimate, not a bound: the kernel verifies
+        // an estimate gets a margin (the kernel verifies and widens); a true bound (kHintIsBound) is used as is
+        const u32 hv = hint & ~kHintIsBound;
+        const u32 hk = (hint & kHintIsBound) ? hv : (u32)min((uint64_t)hv * pp.hint_mul64 / 64u + pp.hint_add, (uint64_t)kPadKFull);
         if (hk < ub) { ub = hk; from_hint = true; }
       }
       if (band > 1) ub = (u32)band;               // test hook: forced initial threshold
@@ -178,7 +180,7 @@ __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const Seq
       int w, l;
       if (lane < 30) { w = 1 + (int)(lane % 5u); l = (int)(lane / 5u); }
       else { w = 6 + (int)(lane - 30u); l = kNumL - 1; }
-      const ShapeCost sc = band_shape_cost(g, w, l);
+      const ShapeCost sc = band_shape_cost(g, w, l, pp);
       key = sc.cost * n_pairs + sc.time * lanes_total;
       best = l * kNumW + w;
     }
@@ -199,10 +201,10 @@ __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const Seq
 }
 
 cudaError_t launch_plan(PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, const uint2* planes, const u32* nplane,
-                        u32* hist, u32 lanes_total, int band, int force_shape, int wedge, cudaStream_t stream) {
+                        u32* hist, u32 lanes_total, int band, int force_shape, int wedge, const PlanParams& pp, cudaStream_t stream) {
   if (n_pairs == 0) return cudaSuccess;
   const u32 blocks = std::min<u32>((n_pairs + 3) / 4, 148u * 16u);
-  plan_kernel<<<blocks, 128, 0, stream>>>(pairs, n_pairs, descs, planes, nplane, hist, lanes_total, band, force_shape, wedge);
+  plan_kernel<<<blocks, 128, 0, stream>>>(pairs, n_pairs, descs, planes, nplane, hist, lanes_total, band, force_shape, wedge, pp);
   return cudaGetLastError();
 }
 

@@ -155,18 +155,24 @@ TRPA_HD uint64_t band_steps(const BandGeom& g, int W, int L) {
   return off + ((S - 1u) % (uint32_t)L) + nblk;
 }
 
-// alu-pipe instructions of one lane-step: 32 columns x (10.4 per word + 14 per column) + the per-step
-// bookkeeping (boundary hand-over, schedule); strip set-up (equality table) per strip
-TRPA_HD uint64_t band_step_ops(int W) { return 32ull * (104ull * (uint64_t)W + 140ull) / 10ull + 150ull; }
-TRPA_HD uint64_t band_setup_ops(int W) { return 120ull + 25ull * (uint64_t)W; }
+// Planner parameters (trpa_set_tuning hooks; results never depend on them).
+//  hint_mul64 / hint_add: band threshold from a distance ESTIMATE = hint * hint_mul64 / 64 + hint_add
+//  cost model, alu-pipe instructions of one lane-step: 32 columns x (word10 / 10 per word + col10 / 10 per
+//  column) + step (boundary hand-over, schedule); strip set-up (equality table, geometry): setup + setup_w * W
+struct PlanParams {
+  uint32_t hint_mul64 = 72, hint_add = 32;
+  uint32_t word10 = 100, col10 = 35, step = 200, setup = 250, setup_w = 25;   // SASS + ncu region counts, profiles/r03_myers3_ncu.md
+};
+TRPA_HD uint64_t band_step_ops(int W, const PlanParams& pp) { return 32ull * ((uint64_t)pp.word10 * (uint64_t)W + pp.col10) / 10ull + pp.step; }
+TRPA_HD uint64_t band_setup_ops(int W, const PlanParams& pp) { return pp.setup + (uint64_t)pp.setup_w * (uint64_t)W; }
 
 struct ShapeCost { uint64_t time, cost; };   // time: alu instructions on the critical lane; cost = time * L
-TRPA_HD ShapeCost band_shape_cost(const BandGeom& g, int widx, int lidx) {
+TRPA_HD ShapeCost band_shape_cost(const BandGeom& g, int widx, int lidx, const PlanParams& pp) {
   const int W = shape_W(widx), L = 1 << lidx;
   const uint32_t mwords = (g.m + 31u) >> 5;
   const uint32_t S = (mwords + W - 1) / W;
   ShapeCost c;
-  c.time = band_steps(g, W, L) * band_step_ops(W) + (uint64_t)((S + L - 1) / L) * band_setup_ops(W);
+  c.time = band_steps(g, W, L) * band_step_ops(W, pp) + (uint64_t)((S + L - 1) / L) * band_setup_ops(W, pp);
   c.cost = c.time * (uint64_t)L;
   return c;
 }

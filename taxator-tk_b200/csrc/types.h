@@ -15,6 +15,9 @@ struct SeqDesc {
   uint32_t pad;
 };
 
+// PairDesc.pad on entry: distance hint; bit 31 set = the value is a true upper bound (no margin needed)
+constexpr uint32_t kHintIsBound = 0x80000000u;
+
 // One pairwise alignment request: getAlignment(A = descs[a], B = descs[b]) -> result slot `out`.
 // pad: distance hint on entry (0 = none); after planning bits 0..7 = kernel shape, bits 8..31 = band
 // threshold k0.  aux: after planning the wedge request (shapes.h wedge_pack: half width at the last

@@ -200,16 +200,7 @@ myers3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __re
     have_pre = false;
   };
   // extra steps between round r and r+1 so that no lane starts a strip before finishing the previous one
-  auto round_gap = [&](u32 rr) -> u32 {
-    u32 gp = 1;
-    for (u32 l = 0; l < (u32)L; ++l) {
-      const u32 st = rr * L + l;
-      if (st + L >= S) break;
-      const int term = (int)gb1(st) - (int)gb0(st + L) + 1 - L;
-      if (term > (int)gp) gp = (u32)term;
-    }
-    return gp;
-  };
+  auto round_gap = [&](u32 rr) -> u32 { return bg.round_gap(rr, (u32)W, (u32)L, S); };
 
   for (;;) {
     if (!active && !exhausted) {  // uniform inside a group

@@ -78,12 +78,12 @@ struct BandGeom {
   uint32_t m, n;
   uint32_t a0, a1;      // half band width at the first / last pattern row (a1 < a0: wedge)
   uint32_t row0;        // wedge: the band keeps its full width up to this pattern row
-  uint32_t taper_q;     // ((a0 - a1) << 20) / (m - row0)
+  uint32_t taper_q;     // ((a0 - a1) << 32) / (m - row0) (slope < 1 column per row); 0 = plain band
   uint32_t k;           // effective threshold; 0xffffffff when the band covers the whole matrix
-  TRPA_HD uint32_t a_at(uint32_t row) const {
-    if (!taper_q || row <= row0) return a0;
-    const uint32_t r = (row < m ? row : m) - row0;
-    return a0 - (uint32_t)(((uint64_t)r * taper_q) >> 20);
+  TRPA_HD uint32_t a_at(uint32_t row) const {   // branch-free: taper_q == 0 gives a0
+    const uint32_t rr = row < m ? row : m;
+    const uint32_t r = rr > row0 ? rr - row0 : 0u;
+    return a0 - (uint32_t)(((uint64_t)r * taper_q) >> 32);
   }
   TRPA_HD uint32_t b0(uint32_t s, uint32_t R) const {
     const uint32_t x = s * R, a = a_at(x);
@@ -92,6 +92,21 @@ struct BandGeom {
   TRPA_HD uint32_t b1(uint32_t s, uint32_t R) const {
     const uint32_t hi = (s + 1u) * R - 1u + (n - m) + a_at(s * R);
     return (hi < n - 1u ? hi : n - 1u) >> 5;
+  }
+  // Extra group steps between round r and r + 1 of the rotating schedule (myers3.cuh): an upper bound of
+  //   max over the strips st of round r with a successor st + L < S of  b1(st) - b0(st + L) + 1 - L
+  // (no lane may start a strip before it finished the previous one; a larger gap only idles).  Two bounds,
+  // both from b0/b1 being non-decreasing in st and a_at non-increasing: the unclipped closed form at the
+  // round's first strip (exact away from the matrix borders), and last-b1 minus first-b0 (exact for L = 1).
+  // All lanes of a group and the planner evaluate exactly this function.
+  TRPA_HD uint32_t round_gap(uint32_t r, uint32_t W, uint32_t L, uint32_t S) const {
+    const uint32_t R = 32u * W, s0 = r * L;
+    if (s0 + L >= S) return 1u;
+    const uint32_t l_hi = (S - L - 1u - s0) < (L - 1u) ? (S - L - 1u - s0) : (L - 1u);
+    const int cf = (int)(((n - m) + a_at(s0 * R) - 1u) >> 5) + (int)((a_at((s0 + L) * R) + 31u) >> 5) - (int)((L - 1u) * (W + 1u));
+    const int b2 = (int)b1(s0 + l_hi, R) - (int)b0(s0 + L, R) + 1 - (int)L;
+    const int g = cf < b2 ? cf : b2;
+    return g > 1 ? (uint32_t)g : 1u;
   }
   TRPA_HD bool wedge() const { return taper_q != 0; }
 };
@@ -119,17 +134,17 @@ TRPA_HD BandGeom band_from_k(uint32_t m, uint32_t n, uint32_t k, bool force_full
     uint32_t a1 = wedge & ((1u << kWedgeA1Bits) - 1u);
     const uint32_t row0 = g.a0 + ((wedge >> kWedgeA1Bits) << 6);
     if (a1 < 32u) a1 = 32u;
-    if (a1 + 16u < g.a0 && row0 + 64u < m) {
+    if (a1 + 16u < g.a0 && row0 + 64u < m && g.a0 - a1 < m - row0) {   // slope < 1: b0 / b1 stay monotonic
       g.a1 = a1; g.row0 = row0;
-      g.taper_q = (uint32_t)((((uint64_t)(g.a0 - a1)) << 20) / (m - row0));
+      g.taper_q = (uint32_t)((((uint64_t)(g.a0 - a1)) << 32) / (m - row0));
       if (!g.taper_q) { g.a1 = g.a0; g.row0 = 0; }
     }
   }
   return g;
 }
 
-// Group steps the rotating schedule needs for one attempt (gap evaluated at both ends of a round;
-// long schedules are sampled: the gap is piecewise linear in the round index).
+// Group steps the rotating schedule needs for one attempt (long schedules are sampled: the gap is
+// piecewise linear in the round index).
 TRPA_HD uint64_t band_steps(const BandGeom& g, int W, int L) {
   const uint32_t R = 32u * (uint32_t)W;
   const uint32_t mwords = (g.m + 31u) >> 5, nblk = (g.n + 31u) >> 5;
@@ -140,16 +155,7 @@ TRPA_HD uint64_t band_steps(const BandGeom& g, int W, int L) {
     const uint32_t stride = rounds > 12u ? (rounds + 11u) / 12u : 1u;
     uint64_t acc = 0;
     uint32_t n = 0;
-    for (uint32_t r = 0; r < rounds; r += stride, ++n) {
-      const uint32_t s0 = r * (uint32_t)L;
-      int gap = 1;
-      const uint32_t l_hi = (S - L - 1u - s0) < (uint32_t)(L - 1) ? (S - L - 1u - s0) : (uint32_t)(L - 1);
-      const int t0 = (int)g.b1(s0, R) - (int)g.b0(s0 + L, R) + 1 - L;
-      const int t1 = (int)g.b1(s0 + l_hi, R) - (int)g.b0(s0 + l_hi + L, R) + 1 - L;
-      if (t0 > gap) gap = t0;
-      if (t1 > gap) gap = t1;
-      acc += (uint64_t)L + (uint64_t)gap;
-    }
+    for (uint32_t r = 0; r < rounds; r += stride, ++n) acc += (uint64_t)L + (uint64_t)g.round_gap(r, (uint32_t)W, (uint32_t)L, S);
     off = acc * rounds / n;
   }
   return off + ((S - 1u) % (uint32_t)L) + nblk;

@@ -48,3 +48,16 @@ def test_no_cpu_fallback():
     with pytest.raises(rpa_b200.TrpaError) as e:
         rpa_b200.Context(0)
     assert "no CPU fallback" in str(e.value)
+
+
+def test_band_geometry_and_schedule(tmp_path):
+    """shapes.h on the host: the closed-form round gap is an upper bound of the exact requirement and the
+    rotating schedule of the banded kernel never double-books a lane (tests/band_geometry_check.cpp)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "band_geometry_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(root, "taxator-tk_b200", "csrc"), "-o", exe,
+                           os.path.join(root, "tests", "band_geometry_check.cpp")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("ok:")

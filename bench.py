@@ -96,7 +96,7 @@ def subset(d, n_queries):
     return s
 
 
-def run_reference_binary(d, threads, keep_dir=None):
+def run_reference_binary(d, threads, keep_dir=None, model_args=None):
     """Times oracle/_ref/taxator (real reference, -DNDEBUG) on the files of d; returns (seconds, sorted GFF3 lines)."""
     binary = os.path.join(ROOT, "oracle", "_ref", "taxator")
     if not os.path.exists(binary):
@@ -109,6 +109,8 @@ def run_reference_binary(d, threads, keep_dir=None):
                "-p", str(threads), "-x", "0.5", "-o", "0"]
         if d.cfg.protein:
             cmd += ["-b", "protein"]
+        if model_args:   # the alignment-free models read no sequence files
+            cmd = [binary] + list(model_args) + ["-g", "mapping.tax", "-p", str(threads), "-o", "0"]
         with open(os.path.join(tmp, "alignments.tsv"), "rb") as fin:
             t0 = time.perf_counter()
             p = subprocess.run(cmd, cwd=tmp, env=env, stdin=fin, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
@@ -195,12 +197,128 @@ def reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def lca_bench(args, rank, local_rank, world):
+    """the alignment-free models (megan-lca with the reference's defaults) on the record tables of
+    C2 (100k segments x 50 records).  HBM-bound streaming kernel: 44 B read per record, 72 B per segment."""
+    w = WORKLOADS["c2"]
+    d = make_data("c2", args.seed + rank, n_queries=args.segments)
+    segs, cands = synth.segments_fast(d)
+    parent, left, right, depth = d.nested_set()
+    n_seg, n_cand = len(segs), len(cands)
+    evalue = np.power(10.0, -np.round(cands["score"].astype(np.float64) / 12.0))
+    kw = dict(toppercent=0.05, minscore=0.0, maxevalue=1000.0, minsupport=1)
+    cores = os.cpu_count() or 1
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sub = subset(d, min(5000, len(d.q_names)))
+        times = []
+        for it in range(args.warmup + args.steps):
+            dt, _ = run_reference_binary(sub, cores, model_args=["-a", "megan-lca"])
+            if dt is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/taxator was not built"}))
+                return
+            if it >= args.warmup:
+                times.append(dt)
+        nseg_sub = len(synth.segments_fast(sub)[0])
+        v = nseg_sub / (sum(times) / len(times))
+        print(json.dumps({"impl": "reference", "metric": "query segments/sec (taxator -a megan-lca)", "value": v, "unit": "segments/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+                          "config": {"workload": "lca: megan-lca on the record tables of c2", "segments_per_step": nseg_sub},
+                          "cpu_baseline": {"value": v, "unit": "segments/s", "cores": cores, "kind": "reference",
+                                           "sample": "%d segments, oracle/_ref/taxator -a megan-lca -p %d, wall incl. start-up" % (nseg_sub, cores)},
+                          "e2e": {"value": v, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+    import torch
+    import rpa_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def reduce(x, op):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    ctx = rpa_b200.Context(local_rank, torch.cuda.current_stream().cuda_stream)
+    ctx.load_taxonomy(parent, left, right, depth, 0)
+    # pinned host tables (the e2e contract: inputs come from pinned host memory every step)
+    pins = [torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).copy()).pin_memory() for a in (segs, cands, evalue)]
+    segs = pins[0].numpy().view(rpa_b200.SEG_DTYPE)
+    cands = pins[1].numpy().view(rpa_b200.CAND_DTYPE)
+    evalue = pins[2].numpy().view(np.float64)
+    for _ in range(max(args.warmup, 3)):
+        ctx.predict_lca_batch(rpa_b200.MODEL_MEGAN_LCA, segs, cands, evalue, None, **kw)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if dist is not None:
+        dist.barrier()
+    # resident: the call uploads once, runs one untimed pass, then `steps` timed launches (CUDA events in the library)
+    res, k_ms = ctx.predict_lca_batch(rpa_b200.MODEL_MEGAN_LCA, segs, cands, evalue, None, repeat=max(args.steps, 2), **kw)
+    k_ms = reduce(k_ms, torch.distributed.ReduceOp.MAX if dist else None)
+    # end to end: host tables in, host results out, every step
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.predict_lca_batch(rpa_b200.MODEL_MEGAN_LCA, segs, cands, evalue, None, **kw)
+    torch.cuda.synchronize()
+    ms_e2e = reduce(1e3 * (time.perf_counter() - t0) / args.steps, torch.distributed.ReduceOp.MAX if dist else None)
+    clocks = sampler.finish()
+    total = reduce(float(n_seg), torch.distributed.ReduceOp.SUM if dist else None)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    h2d = n_cand * (36 + 8) + n_seg * 16
+    alg_bytes = h2d + n_seg * 56
+    gbs = alg_bytes / (k_ms / 1e3) / 1e9
+    line = {"metric": "query segments/sec (taxator -a megan-lca)", "value": total / (k_ms / 1e3), "unit": "segments/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": k_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+            "config": {"workload": "lca: megan-lca (-t 0.05 -m 0 -e 1000 -c 1) on the record tables of c2", "segments_per_gpu": n_seg,
+                       "candidates_per_gpu": n_cand, "l2": "tables (%.0f MB) larger than L2" % (alg_bytes / 1e6), "seed": args.seed},
+            "e2e": {"value": total / (ms_e2e / 1e3), "unit": "segments/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(n_seg * 56)},
+            "roofline": {"bound": "hbm", "kernel": "lca_models_kernel", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": gbs / hbm_peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "algorithmic_bytes_per_launch": alg_bytes},
+            "gpu_launches": int(args.steps), "clocks": clocks}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sub = subset(d, min(5000, len(d.q_names)))
+        dt, ref_lines = run_reference_binary(sub, cores, model_args=["-a", "megan-lca"])
+        if dt is not None:
+            nsub = len(synth.segments_fast(sub)[0])
+            q_len = np.array([len(x) for x in d.q_seqs], np.uint32)
+            ours = sorted(gff3.render(res[:nsub], segs[:nsub], d.q_names, q_len, parent, depth, [str(t) for t in d.tax_ids]))
+            line["cpu_baseline"] = {"value": nsub / dt, "unit": "segments/s", "cores": cores, "kind": "reference",
+                                    "sample": "first %d segments; oracle/_ref/taxator -a megan-lca -p %d, wall %.2f s incl. start-up and parsing" % (nsub, cores, dt),
+                                    "gff3_identical_to_gpu": ours == ref_lines}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["lca"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--segments", type=int, default=None, help="override segments per GPU (debug)")
@@ -214,6 +332,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if args.workload == "lca":
+        lca_bench(args, rank, local_rank, world)
+        return
     if args.impl == "reference":
         reference_arm(args, rank, world)
         return

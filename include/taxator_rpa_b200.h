@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TRPA_ABI_VERSION 4
+#define TRPA_ABI_VERSION 5
 
 #define TRPA_OK 0
 #define TRPA_ERR_CUDA (-1)
@@ -72,6 +72,7 @@ typedef struct trpa_segment {
 #define TRPA_KIND_SINGLE 1    /* n==1: hh:371-388 */
 #define TRPA_KIND_IDENTICAL 2 /* full-length 100% hit shortcut: hh:431-472 */
 #define TRPA_KIND_PLACED 3    /* three-pass placement: hh:474-837 */
+#define TRPA_KIND_LCA 4       /* point estimate of an alignment-free model (trpa_predict_lca_batch) */
 
 /* == the PredictionRecord fields predict() sets (core/src/predictionrecord.hh:38-167) plus the
  * STATS counters of hh:834-837. */
@@ -157,6 +158,34 @@ int trpa_batch_upload(trpa_ctx* ctx, const trpa_segment* segs, uint32_t n_segs, 
                       uint32_t n_cands);
 int trpa_batch_run(trpa_ctx* ctx);
 int trpa_batch_download(trpa_ctx* ctx, trpa_result* out);
+
+/* ---- the alignment-free placement models behind the same predict() interface ------------------ */
+/* DummyPredictionModel, LCASimplePredictionModel, MeganLCAPredictionModel, NBestLCAPredictionModel
+ * (core/src/taxonpredictionmodel.hh:57-259) as taxator.cpp:346-361 builds them (treat_unclassified = false;
+ * "ic-megan-lca" is the same model as "megan-lca" there).  Fields = the command line options they read. */
+#define TRPA_MODEL_DUMMY 0
+#define TRPA_MODEL_SIMPLE_LCA 1
+#define TRPA_MODEL_MEGAN_LCA 2
+#define TRPA_MODEL_NBEST_LCA 3
+typedef struct trpa_lca_params {
+  uint32_t model;
+  float toppercent;               /* -t: MinScoreMaxEvalueTopPercentFilter (alignmentsfilter.hh:349-386) */
+  float minscore;                 /* -m */
+  float maxevalue;                /* -e, narrowed to float like the filter's constructor argument (:351) */
+  uint32_t minsupport;            /* -c */
+  uint32_t nbest;                 /* -n: NumBestBitscoreFilter (alignmentsfilter.hh:493-534) */
+  uint32_t ignore_unclassified;   /* -u: RemoveUnclassifiedFilter (alignmentsfilter.hh:612-623) */
+  uint32_t reserved;
+} trpa_lca_params;
+/* Same segment / candidate tables as trpa_predict_batch (unmasked records, record-set order; only qstart,
+ * qstop, score and node are read).  evalue: one double per candidate (nullable: 0); node_unclassified: one
+ * byte per taxonomy node (TaxonAnnotation is_unclassified, ncbidata.cpp:119-126; nullable).  Results:
+ * kind TRPA_KIND_LCA (qrstart/qrstop, lower == upper node, rtax, support = feature width; ival = -1: these
+ * models never set it) or TRPA_KIND_NONE (setUnclassified; the feature range stays the whole query).
+ * repeat > 1 re-runs the kernel for timing; kernel_ms (nullable) = device ms per run. */
+int trpa_predict_lca_batch(trpa_ctx* ctx, const trpa_lca_params* params, const trpa_segment* segs, uint32_t n_segs,
+                           const trpa_candidate* cands, uint32_t n_cands, const double* evalue,
+                           const uint8_t* node_unclassified, trpa_result* out, int repeat, double* kernel_ms);
 
 /* ---- lower-level entry points (unit tests, micro-benchmarks) ------------------------------ */
 /* edit distance of n_pairs pairs over a private ASCII sequence table; == getAlignmentDNA distance

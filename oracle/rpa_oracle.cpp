@@ -574,4 +574,98 @@ int orc_predict_segment(
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The alignment-free placement models (core/src/taxonpredictionmodel.hh:57-259) with their filters
+// (core/src/alignmentsfilter.hh:349-386, :493-534, :612-623), restated record by record on a std::list
+// with a `filtered` flag like AlignmentRecord::filterOut(); node sets are std::set like the reference's
+// std::set<const TaxonNode*> (the LCA of a set does not depend on its order).
+// model: 0 dummy, 1 simple-lca, 2 megan-lca (== ic-megan-lca, taxator.cpp:352-357), 3 n-best-lca.
+// evalue / unclassified may be null.  The result's kind is 4 (point estimate) or 0 (setUnclassified).
+int orc_predict_lca_model(const uint32_t* parent, const uint32_t* left, const uint32_t* right, const uint8_t* depth,
+                          uint32_t n_nodes, uint32_t root, uint32_t model, float toppercent, float minscore,
+                          double maxevalue_arg, uint32_t minsupport, uint32_t nbest, int ignore_unclassified,
+                          const OrcCand* cands, const double* evalue, uint32_t n, const uint8_t* unclassified,
+                          OrcResult* res) {
+  Tax tax{parent, left, right, depth, n_nodes, root};
+  struct Rec { float score; double evalue; uint32_t qstart, qstop, node; bool filtered; };
+  std::list<Rec> recordset;
+  for (uint32_t i = 0; i < n; ++i)
+    recordset.push_back(Rec{cands[i].score, evalue ? evalue[i] : 0.0, cands[i].qstart, cands[i].qstop, cands[i].node, false});
+  memset(res, 0, sizeof(*res));
+  res->ival = -1.f;   // never set by these models: PredictionRecordBase starts at -1 (predictionrecord.hh:40)
+  auto set_unclassified = [&]() {   // taxonpredictionmodel.hh:46-49 after initPredictionRecord (:42-44)
+    res->kind = 0; res->lower = res->upper = res->rtax = root; res->support = 0; res->qrstart = 1; res->qrstop = 0;
+  };
+  auto lca_set = [&](const std::set<uint32_t>& nodes) -> uint32_t {   // taxonomyinterface.hh:61-74
+    auto it = nodes.begin();
+    uint32_t tmp = *it++;
+    while (it != nodes.end()) { tmp = lca(tax, tmp, *it); ++it; }
+    return tmp;
+  };
+  auto lca_simple = [&]() {   // LCASimplePredictionModel::predict, taxonpredictionmodel.hh:73-125
+    std::set<uint32_t> refnodes, refnodes_best;
+    auto rec_it = recordset.begin();
+    while (rec_it != recordset.end() && rec_it->filtered) ++rec_it;   // firstUnmaskedIter
+    if (rec_it == recordset.end()) { set_unclassified(); return; }
+    uint32_t qrstart = rec_it->qstart, qrstop = rec_it->qstop;
+    float maxscore = rec_it->score;
+    if (qrstart > qrstop) std::swap(qrstart, qrstop);
+    refnodes.insert(rec_it->node);
+    ++rec_it;
+    for (; rec_it != recordset.end(); ++rec_it) {
+      if (!rec_it->filtered) {
+        if (rec_it->qstart <= rec_it->qstop) { qrstart = std::min(rec_it->qstart, qrstart); qrstop = std::max(rec_it->qstop, qrstop); }
+        else { qrstart = std::min(rec_it->qstop, qrstart); qrstop = std::max(rec_it->qstart, qrstop); }
+        if (rec_it->score > maxscore) maxscore = rec_it->score;
+        refnodes.insert(rec_it->node);
+      }
+    }
+    for (auto& r : recordset) if (!r.filtered && r.score == maxscore) refnodes_best.insert(r.node);
+    const uint32_t node = lca_set(refnodes);
+    res->kind = 4; res->qrstart = qrstart; res->qrstop = qrstop;
+    res->lower = res->upper = node; res->support = qrstop - qrstart + 1;   // setNodePoint(node): feature width
+    res->rtax = refnodes.size() != refnodes_best.size() ? lca_set(refnodes_best) : node;
+  };
+  if (model == 0) { set_unclassified(); return 0; }
+  if (model == 1) { lca_simple(); return 0; }
+  if (model == 2) {
+    // MinScoreMaxEvalueTopPercentFilter (alignmentsfilter.hh:351: the constructor takes maxevalue as float)
+    const float maxevalue = (float)maxevalue_arg;
+    float max_bitscore = .0;
+    unsigned int support = 0;
+    for (auto& r : recordset) {
+      if (!r.filtered) {
+        if (r.score < minscore || r.evalue > maxevalue) r.filtered = true;
+        else if (r.score > max_bitscore) { max_bitscore = r.score; support++; }
+      }
+    }
+    max_bitscore = (1.0 - toppercent) * max_bitscore;
+    for (auto& r : recordset) if (r.score < max_bitscore) r.filtered = true;
+    if (ignore_unclassified) for (auto& r : recordset) if (unclassified && unclassified[r.node]) r.filtered = true;
+    if (support >= minsupport) { lca_simple(); return 0; }
+    set_unclassified();
+    return 0;
+  }
+  if (model == 3) {
+    // NumBestBitscoreFilter (alignmentsfilter.hh:497-527)
+    std::multimap<float, Rec*, std::greater<float>> sorted_bitscores;
+    for (auto& r : recordset) if (!r.filtered) sorted_bitscores.insert(std::make_pair(r.score, &r));
+    if (!sorted_bitscores.empty()) {
+      unsigned int count = nbest;
+      auto sb_it = sorted_bitscores.begin();
+      float lastvalue = sb_it++->first;
+      for (; sb_it != sorted_bitscores.end(); ++sb_it) {
+        if (sb_it->first != lastvalue) {
+          if (--count <= 0) break;
+          lastvalue = sb_it->first;
+        }
+      }
+      for (; sb_it != sorted_bitscores.end(); ++sb_it) sb_it->second->filtered = true;
+    }
+    lca_simple();
+    return 0;
+  }
+  return -1;
+}
+
 }  // extern "C"

@@ -1234,6 +1234,55 @@ int trpa_fetch_segments(trpa_ctx* c, const uint32_t* ref_seq, const uint32_t* st
   return 0;
 }
 
+int trpa_predict_lca_batch(trpa_ctx* c, const trpa_lca_params* pp, const trpa_segment* segs, uint32_t n_segs,
+                           const trpa_candidate* cands, uint32_t n_cands, const double* evalue,
+                           const uint8_t* node_unclassified, trpa_result* out, int repeat, double* kernel_ms) {
+  if (!c || !pp || (n_segs && (!segs || !out)) || (n_cands && !cands)) { set_error("bad arguments"); return TRPA_ERR_ARG; }
+  if (pp->model > TRPA_MODEL_NBEST_LCA) { set_error("unknown placement model"); return TRPA_ERR_ARG; }
+  if (c->n_nodes == 0) { set_error("taxonomy not loaded"); return TRPA_ERR_STATE; }
+  if (use_device(c)) return TRPA_ERR_CUDA;
+  if (kernel_ms) *kernel_ms = 0.0;
+  if (n_segs == 0) return 0;
+  // one validation pass over the tables (the same contract as trpa_batch_upload: contiguous record sets)
+  u64 expect = 0;
+  for (u32 s = 0; s < n_segs; ++s) {
+    if (segs[s].cand_begin != expect || (u64)segs[s].cand_begin + segs[s].cand_count > n_cands) {
+      set_error("segment table: candidate ranges must be contiguous and inside the candidate table");
+      return TRPA_ERR_ARG;
+    }
+    expect += segs[s].cand_count;
+  }
+  for (u32 i = 0; i < n_cands; ++i)
+    if (cands[i].node >= c->n_nodes) { set_error("candidate node out of range"); return TRPA_ERR_ARG; }
+  DevBuf<trpa_segment> d_segs; DevBuf<trpa_candidate> d_cands; DevBuf<double> d_ev; DevBuf<uint8_t> d_un; DevBuf<trpa_result> d_out;
+  if (d_segs.ensure(n_segs) || d_cands.ensure(n_cands + 1) || d_out.ensure(n_segs) || (evalue && d_ev.ensure(n_cands + 1)) ||
+      (node_unclassified && d_un.ensure(c->n_nodes)))
+    return TRPA_ERR_NOMEM;
+  CK(cudaMemcpyAsync(d_segs.p, segs, sizeof(trpa_segment) * n_segs, cudaMemcpyHostToDevice, c->stream));
+  if (n_cands) CK(cudaMemcpyAsync(d_cands.p, cands, sizeof(trpa_candidate) * n_cands, cudaMemcpyHostToDevice, c->stream));
+  if (evalue && n_cands) CK(cudaMemcpyAsync(d_ev.p, evalue, sizeof(double) * n_cands, cudaMemcpyHostToDevice, c->stream));
+  if (node_unclassified) CK(cudaMemcpyAsync(d_un.p, node_unclassified, c->n_nodes, cudaMemcpyHostToDevice, c->stream));
+  if (repeat < 1) repeat = 1;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const Taxonomy tax = dev_tax(c);
+  if (kernel_ms && repeat > 1)   // one untimed pass when timing is requested
+    CK(launch_lca_models(d_segs.p, n_segs, d_cands.p, evalue ? d_ev.p : nullptr, node_unclassified ? d_un.p : nullptr, tax, *pp, d_out.p, c->stream));
+  CK(cudaEventRecord(e0, c->stream));
+  for (int r = 0; r < repeat; ++r)
+    CK(launch_lca_models(d_segs.p, n_segs, d_cands.p, evalue ? d_ev.p : nullptr, node_unclassified ? d_un.p : nullptr, tax, *pp, d_out.p, c->stream));
+  CK(cudaEventRecord(e1, c->stream));
+  CK(cudaMemcpyAsync(out, d_out.p, sizeof(trpa_result) * n_segs, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  if (kernel_ms) *kernel_ms = ms / repeat;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  c->prof.launches_other += (u64)repeat;
+  d_segs.release(); d_cands.release(); d_ev.release(); d_un.release(); d_out.release();
+  return 0;
+}
+
 int trpa_lca_batch(trpa_ctx* c, const uint32_t* a, const uint32_t* b, uint32_t n, uint32_t* out) {
   if (!c || !a || !b || !out) { set_error("bad arguments"); return TRPA_ERR_ARG; }
   if (c->n_nodes == 0) { set_error("taxonomy not loaded"); return TRPA_ERR_STATE; }

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "shapes.h"
+#include "taxator_rpa_b200.h"
 
 namespace trpa {
 
@@ -23,6 +24,12 @@ cudaError_t launch_plan(PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, cons
 cudaError_t launch_myers3(int shape, const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint2* planes,
                           const u32* nplane, const uint2* codes, int* out, uint4* scratch, u32 scratch_stride, u32* cursor,
                           unsigned long long* stats, int force_full, u32* slots_out, cudaStream_t stream);
+
+// alignment-free placement models (lca_models.cu); Taxonomy: machine.h
+struct Taxonomy;
+cudaError_t launch_lca_models(const trpa_segment* segs, u32 n_segs, const trpa_candidate* cands, const double* evalue,
+                              const uint8_t* uncl, const Taxonomy& tax, const trpa_lca_params& pp, trpa_result* out,
+                              cudaStream_t stream);
 
 // BLOSUM62 linear-gap NW with traced length; out2[pair.out] = {mutual, #diagonal steps}
 // scratch: scratch_stride int2 per pair, needed only when a pair's A is longer than 512 residues

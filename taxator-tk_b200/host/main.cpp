@@ -13,6 +13,7 @@
 #include "driver.h"
 #include "ingest.h"
 #include "records.h"
+#include "lca_model.h"
 #include "rpa_model.h"
 #include "seqstore.h"
 #include "taxonomy.h"
@@ -27,6 +28,11 @@ struct Options {
   unsigned processors = 1;
   bool split_alignments = true, alignments_sorted = false, delete_unmarked = true;
   float filterout = 0.5f, toppercent = 0.05f;
+  // the alignment-free models' options (taxator.cpp:287-292)
+  double maxevalue = 1000.0;
+  unsigned minsupport = 1, nbest = 1;
+  float minscore = 0.0f;
+  bool ignore_unclassified = false;
   std::vector<int> gpus = {0};
   size_t batch_segments = 200000;
   size_t batch_bytes = 128u << 20;
@@ -39,7 +45,7 @@ static void usage(std::ostream& os) {
   os << "Allowed options:\n"
         "  -h [ --help ]                     show help message\n"
         "  -V [ --version ]                  show program version\n"
-        "  -a [ --algorithm ] arg (=rpa)     only rpa is accelerated by this build\n"
+        "  -a [ --algorithm ] arg (=rpa)     rpa, simple-lca, megan-lca, ic-megan-lca, n-best-lca, dummy\n"
         "  -g [ --seqid-taxid-mapping ] arg  filename of seqid->taxid mapping for reference\n"
         "  -q [ --query-sequences ] arg      query sequences FASTA\n"
         "  -v [ --query-sequences-index ] arg  query sequences FASTA index\n"
@@ -53,7 +59,12 @@ static void usage(std::ostream& os) {
         "  -o [ --alignments-sorted ] arg (=0)\n"
         "  -d [ --delete-notranks ] arg (=1)\n"
         "  -x [ --heuristic-cutoff ] arg (=0.5)\n"
-        "  -t [ --toppercent ] arg (=0.05)\n"
+        "  -t [ --toppercent ] arg (=0.05)   RPA re-evaluation band or top percent parameter for LCA methods\n"
+        "  -e [ --max-evalue ] arg (=1000)   maximum evalue (megan-lca)\n"
+        "  -c [ --min-support ] arg (=1)     minimum support (megan-lca)\n"
+        "  -m [ --minscore ] arg (=0)        minimum score (megan-lca)\n"
+        "  -n [ --nbest ] arg (=1)           n-best-lca parameter\n"
+        "  -u [ --ignore-unclassified ]      ignore alignments to (partly) unclassified taxa (megan-lca)\n"
         "  --gpus arg (=0)                   comma separated CUDA device indices to shard segments over\n"
         "  --batch-segments arg (=200000)    record sets per GPU batch (record-at-a-time ingest)\n"
         "  --batch-bytes arg (=134217728)    alignment text per GPU batch (fast ingest)\n"
@@ -77,7 +88,7 @@ static int parse_args(int argc, char** argv, Options& o) {
     {"processors", 'p'}, {"logfile", 'l'}, {"dataformat", 'b'}, {"ranks", 'r'}, {"split-alignments", 's'},
     {"alignments-sorted", 'o'}, {"delete-notranks", 'd'}, {"heuristic-cutoff", 'x'}, {"toppercent", 't'},
     {"gpus", 'G'}, {"batch-segments", 'B'}, {"timing", 'T'}, {"batch-bytes", 'Y'}, {"legacy-ingest", 'L'}, {"write-refpack", 'W'}, {"write-querypack", 'Q'},
-    // accepted and ignored (other models' knobs)
+    // the alignment-free models' knobs; -w is accepted and ignored
     {"max-evalue", 'e'}, {"min-support", 'c'}, {"minscore", 'm'}, {"nbest", 'n'}, {"db-whitelist", 'w'},
     {"ignore-unclassified", 'u'}, {"citation", 'C'}, {"advanced-options", 'A'}};
   for (int i = 1; i < argc; ++i) {
@@ -134,7 +145,11 @@ static int parse_args(int argc, char** argv, Options& o) {
       case 'W': o.write_refpack = need(); break;
       case 'Q': o.write_querypack = need(); break;
       case 'T': o.timing = true; break;
-      case 'u': break;
+      case 'u': o.ignore_unclassified = true; break;
+      case 'e': o.maxevalue = std::stod(need()); break;
+      case 'c': o.minsupport = (unsigned)std::stoul(need()); break;
+      case 'm': o.minscore = std::stof(need()); break;
+      case 'n': o.nbest = (unsigned)std::stoul(need()); break;
       default: need(); break;  // ignored options with a value
     }
   }
@@ -152,8 +167,28 @@ int main(int argc, char** argv) {
       return EXIT_FAILURE;
     }
     if (opt.algorithm != "rpa") {
-      std::cout << "this build accelerates only the rpa algorithm; use the reference taxator for: " << opt.algorithm << std::endl;
-      return EXIT_FAILURE;
+      // the alignment-free models (taxator.cpp:346-361): no sequence stores, records one set at a time
+      trpa_lca_params params;
+      if (opt.algorithm == "dummy") params = LCAPredictionModelGPU::dummy();
+      else if (opt.algorithm == "simple-lca") params = LCAPredictionModelGPU::simple();
+      else if (opt.algorithm == "megan-lca" || opt.algorithm == "ic-megan-lca")
+        params = LCAPredictionModelGPU::megan(opt.ignore_unclassified, opt.toppercent, opt.minscore, (int)opt.minsupport, opt.maxevalue);
+      else if (opt.algorithm == "n-best-lca") params = LCAPredictionModelGPU::nbest((int)opt.nbest);
+      else {
+        std::cout << "classification algorithm can either be: rpa (default), simple-lca, megan-lca, ic-megan-lca, n-best-lca" << std::endl;
+        return EXIT_FAILURE;
+      }
+      FlatTaxonomy tax = load_taxonomy_from_environment(opt.ranks, opt.delete_unmarked);
+      SeqIdMapping mapping = load_mapping(opt.mapping);
+      std::ofstream logsink(opt.logfile.c_str(), std::ios_base::app);
+      LCAPredictionModelGPU model(&tax, params, opt.gpus.empty() ? 0 : opt.gpus[0]);
+      std::ios::sync_with_stdio(false);
+      RecordSetReader reader(std::cin, mapping, tax, opt.split_alignments, opt.alignments_sorted);
+      run_prediction_stream(
+          reader, tax, opt.batch_segments,
+          [&](std::vector<RecordSet>& sets, std::vector<PredictionRecord>& precs, std::ostream& log) { model.predictBatch(sets, precs, log); },
+          std::cout, logsink);
+      return EXIT_SUCCESS;
     }
     if (opt.dataformat != "nucleotide" && opt.dataformat != "protein") {
       std::cout << "data format can either be nucleotide or protein" << std::endl;

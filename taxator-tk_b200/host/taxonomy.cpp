@@ -99,34 +99,36 @@ FlatTaxonomy load_ncbi_taxonomy(const std::string& nodes_file, const std::string
   }
   FlatTaxonomy T;
   // iterative DFS from the root; `kept_parent` = nearest kept ancestor in the output index space
-  struct Frame { uint32_t raw; uint32_t out; size_t next; bool kept; };
-  auto add_node = [&](uint32_t r, uint32_t parent_out, uint8_t d) {
+  struct Frame { uint32_t raw; uint32_t out; size_t next; bool kept; bool uncl; };
+  auto add_node = [&](uint32_t r, uint32_t parent_out, uint8_t d, bool uncl) {
     const uint32_t id = (uint32_t)T.parent.size();
     T.parent.push_back(parent_out == UINT32_MAX ? id : parent_out);
-    T.left.push_back(0); T.right.push_back(0); T.depth.push_back(d);
+    T.left.push_back(0); T.right.push_back(0); T.depth.push_back(d); T.unclassified.push_back(uncl ? 1 : 0);
     T.taxid.push_back(raw[r].taxid); T.name.push_back(raw[r].name); T.rank.push_back(raw[r].rank);
     T.index[raw[r].taxid] = id;
     return id;
   };
   uint32_t counter = 0;
   std::vector<Frame> st;
-  const uint32_t root_out = add_node(raw_root, UINT32_MAX, 0);
+  const uint32_t root_out = add_node(raw_root, UINT32_MAX, 0, false);
   T.root = root_out;
   T.left[root_out] = ++counter;
-  st.push_back(Frame{raw_root, root_out, 0, true});
+  st.push_back(Frame{raw_root, root_out, 0, true, false});
   while (!st.empty()) {
     Frame& fr = st.back();
     if (fr.next < kids[fr.raw].size()) {
       const uint32_t c = kids[fr.raw][fr.next++];
       const bool keep = !delete_unmarked || keep_ranks.count(raw[c].rank) > 0;
+      const bool uncl = fr.uncl || raw[c].name.find("unclassified") != std::string::npos;
+      const uint32_t parent_frame_out = fr.out;
       if (keep) {
         const uint32_t parent_out = fr.out;
         if (T.depth[parent_out] >= 62) throw ParsingError("taxonomy deeper than 62 levels is not supported");
-        const uint32_t id = add_node(c, parent_out, (uint8_t)(T.depth[parent_out] + 1));
+        const uint32_t id = add_node(c, parent_out, (uint8_t)(T.depth[parent_out] + 1), uncl);
         T.left[id] = ++counter;
-        st.push_back(Frame{c, id, 0, true});
+        st.push_back(Frame{c, id, 0, true, uncl});
       } else {
-        st.push_back(Frame{c, fr.out, 0, false});  // dropped: its children attach to the same kept ancestor
+        st.push_back(Frame{c, parent_frame_out, 0, false, uncl});  // dropped: its children attach to the same kept ancestor
       }
     } else {
       if (fr.kept) T.right[fr.out] = ++counter;

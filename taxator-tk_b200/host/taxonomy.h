@@ -26,6 +26,8 @@ extern const std::vector<std::string> kDefaultRanks;  // core/src/constants.hh:3
 struct FlatTaxonomy {
   std::vector<uint32_t> parent, left, right;
   std::vector<uint8_t> depth;
+  std::vector<uint8_t> unclassified;   // Taxon::is_unclassified (ncbidata.cpp:119-126): the name of the node or of any
+                                       // ancestor in the FULL tree (the root excepted) contains "unclassified"
   std::vector<std::string> taxid, name, rank;
   std::unordered_map<std::string, uint32_t> index;  // taxid -> node
   uint32_t root = 0;

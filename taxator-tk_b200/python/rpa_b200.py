@@ -33,10 +33,20 @@ class Profile(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+MODEL_DUMMY, MODEL_SIMPLE_LCA, MODEL_MEGAN_LCA, MODEL_NBEST_LCA = 0, 1, 2, 3
+KIND_NONE, KIND_SINGLE, KIND_IDENTICAL, KIND_PLACED, KIND_LCA = 0, 1, 2, 3, 4
+
+
+class LcaParams(ctypes.Structure):     # trpa_lca_params
+    _fields_ = [("model", ctypes.c_uint32), ("toppercent", ctypes.c_float), ("minscore", ctypes.c_float),
+                ("maxevalue", ctypes.c_float), ("minsupport", ctypes.c_uint32), ("nbest", ctypes.c_uint32),
+                ("ignore_unclassified", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
 EXPORTS = ["trpa_abi_version", "trpa_last_error", "trpa_create", "trpa_destroy", "trpa_set_params",
            "trpa_set_arena_bytes", "trpa_set_lookahead", "trpa_set_band", "trpa_set_tuning", "trpa_profile_reset", "trpa_profile_get", "trpa_load_taxonomy", "trpa_load_store", "trpa_store_info", "trpa_export_store", "trpa_load_store_packed",
            "trpa_predict_batch", "trpa_batch_upload", "trpa_batch_run", "trpa_batch_download",
-           "trpa_edit_distance_batch", "trpa_protein_align_batch", "trpa_fetch_segments", "trpa_lca_batch",
+           "trpa_predict_lca_batch", "trpa_edit_distance_batch", "trpa_protein_align_batch", "trpa_fetch_segments", "trpa_lca_batch",
            "trpa_int_alu_peak"]
 
 _lib = None
@@ -195,6 +205,23 @@ class Context:
         self._ck(self.L.trpa_fetch_segments(self.h, *[_p(a) for a in arrs], ctypes.c_uint32(n), _p(out),
                                             ctypes.c_uint64(cap), _p(ooff), _p(olen)))
         return [out[int(o):int(o) + int(l)] for o, l in zip(ooff, olen)]
+
+    def predict_lca_batch(self, model, segs, cands, evalue=None, unclassified=None, toppercent=0.05, minscore=0.0,
+                          maxevalue=1000.0, minsupport=1, nbest=1, ignore_unclassified=False, repeat=1):
+        """The alignment-free models (MODEL_DUMMY / SIMPLE_LCA / MEGAN_LCA / NBEST_LCA) on the loaded taxonomy.
+        Returns (results, device ms per run)."""
+        segs = np.ascontiguousarray(segs, SEG_DTYPE); cands = np.ascontiguousarray(cands, CAND_DTYPE)
+        pp = LcaParams(int(model), float(toppercent), float(minscore), float(np.float32(maxevalue)), int(minsupport),
+                       int(nbest), int(bool(ignore_unclassified)), 0)
+        ev = None if evalue is None else np.ascontiguousarray(evalue, np.float64)
+        un = None if unclassified is None else np.ascontiguousarray(unclassified, np.uint8)
+        out = np.zeros(len(segs), RESULT_DTYPE)
+        ms = ctypes.c_double(0)
+        self._ck(self.L.trpa_predict_lca_batch(self.h, ctypes.byref(pp), _p(segs), ctypes.c_uint32(len(segs)), _p(cands),
+                                               ctypes.c_uint32(len(cands)), None if ev is None else _p(ev),
+                                               None if un is None else _p(un), _p(out), ctypes.c_int(int(repeat)),
+                                               ctypes.byref(ms)))
+        return out, ms.value
 
     def lca_batch(self, a, b):
         a = np.ascontiguousarray(a, np.uint32); b = np.ascontiguousarray(b, np.uint32)

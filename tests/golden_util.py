@@ -26,3 +26,78 @@ def render_sorted(fd, results):
     taxids = [str(t) for t in d.tax_ids]
     lines = gff3.render(results, fd.segs, d.q_names, fd.q_len, fd.parent, fd.depth, taxids)
     return sorted(lines)
+
+
+# ---------------------------------------------------------------- alignment-free models (simple-lca, megan-lca, ...)
+# Variants of the golden cases for the models of core/src/taxonpredictionmodel.hh:57-259: scores quantised so that
+# ties occur (best-score sets, n-best distinct values), an e-value column that varies, and some taxa named
+# "unclassified ..." (inherited by their descendants, ncbidata.cpp:119-126).  Used by make_golden_lca.py (reference
+# binary -> tests/golden/lca_<case>_<variant>.gff3) and by the tests, so both see the same inputs.
+LCA_CASES = ("nt_small", "nt_1kb")
+LCA_VARIANTS = {
+    "dummy": (["-a", "dummy"], dict(model=0)),
+    "simple": (["-a", "simple-lca"], dict(model=1)),
+    "megan_default": (["-a", "megan-lca"], dict(model=2, toppercent=0.05, minscore=0.0, maxevalue=1000.0, minsupport=1)),
+    # -c stays 1 in the golden runs: the filter's support counts the rises of the running maximum in record-set
+    # order, and the reference orders records of equal (qstart, qstop) by HEAP ADDRESS (std::sort on a tuple whose
+    # third member is the record pointer, alignmentrecord.hh:479), so its -c >= 2 output is allocator dependent
+    "megan_strict": (["-a", "megan-lca", "-t", "0.3", "-m", "120", "-e", "1e-9", "-c", "1"],
+                     dict(model=2, toppercent=0.3, minscore=120.0, maxevalue=1e-9, minsupport=1)),
+    "megan_uncl": (["-a", "ic-megan-lca", "-t", "0.5", "-u"],
+                   dict(model=2, toppercent=0.5, minscore=0.0, maxevalue=1000.0, minsupport=1, ignore_unclassified=True)),
+    "nbest1": (["-a", "n-best-lca", "-n", "1"], dict(model=3, nbest=1)),
+    "nbest3": (["-a", "n-best-lca", "-n", "3"], dict(model=3, nbest=3)),
+}
+
+
+def lca_case_data(name):
+    """(SynthData with quantised scores, evalue per record in FILE order, unclassified-name flag per node)."""
+    import numpy as np
+    d = case_data(name)
+    sc = d.rec["score"].astype(np.float64)
+    d.rec["score"] = (np.round(sc / 8.0) * 8.0).astype(np.float32)
+    evalue = np.power(10.0, -np.round(d.rec["score"].astype(np.float64) / 12.0))
+    named = np.array([(i % 11) == 5 and i != 0 for i in range(len(d.tax_ids))], bool)
+    return d, evalue, named
+
+
+def lca_unclassified_flags(d, named):
+    """Taxon::is_unclassified: own name or any ancestor's name (the root excepted) contains 'unclassified'."""
+    import numpy as np
+    n = len(d.tax_ids)
+    out = np.zeros(n, np.uint8)
+    for i in range(1, n):          # parents precede children in the synthetic taxonomy (index order)
+        p = int(d.tax_parent[i])
+        assert p < i
+        out[i] = 1 if (named[i] or out[p]) else 0
+    return out
+
+
+def lca_write_files(d, evalue, named, outdir):
+    """nodes/names/mapping/alignments as the reference's taxator reads them (no sequence files needed)."""
+    os.makedirs(outdir, exist_ok=True)
+    d.write_files(outdir)
+    with open(os.path.join(outdir, "names.dmp"), "w") as f:
+        for i, t in enumerate(d.tax_ids):
+            f.write("%d\t|\t%snode%d\t|\t\t|\tscientific name\t|\n" % (t, "unclassified " if named[i] else "", t))
+    r = d.rec
+    with open(os.path.join(outdir, "alignments.tsv"), "w") as f:
+        for k in range(len(r["q"])):
+            qi = r["q"][k]
+            f.write("%s\t%d\t%d\t%d\t%s\t%d\t%d\t%s\t%s\t%d\t%d\n" % (
+                d.q_names[qi], r["qstart"][k], r["qstop"][k], len(d.q_seqs[qi]), d.ref_names[r["r"][k]], r["rstart"][k],
+                r["rstop"][k], repr(float(r["score"][k])), repr(float(evalue[k])), r["ident"][k], r["alnlen"][k]))
+
+
+def lca_flat(d, evalue):
+    """segment / candidate tables + evalue in CANDIDATE order (same ordering as SynthData.segments())."""
+    import numpy as np
+    r = d.rec
+    nrec = len(r["q"])
+    order = np.lexsort((np.arange(nrec), r["qstop"], r["qstart"], r["q"]))
+    segs, cands = d.segments()
+    return segs, cands, np.ascontiguousarray(evalue[order])
+
+
+def lca_golden_lines(case, variant):
+    return open(os.path.join(GOLDEN, "lca_%s_%s.gff3" % (case, variant))).readlines()

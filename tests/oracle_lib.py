@@ -178,3 +178,27 @@ def results_equal(a, b, fields=RESULT_FIELDS):
         if ne.any():
             bad.append((f, np.flatnonzero(ne)[:5].tolist()))
     return bad
+
+
+def oracle_predict_lca(parent, left, right, depth, segs, cands, evalue=None, unclassified=None, model=1, toppercent=0.05,
+                       minscore=0.0, maxevalue=1000.0, minsupport=1, nbest=1, ignore_unclassified=False):
+    """The alignment-free models (oracle/rpa_oracle.cpp orc_predict_lca_model), one call per segment."""
+    O = oracle()
+    f = O.orc_predict_lca_model
+    f.restype = ctypes.c_int
+    n = len(segs)
+    res = np.zeros(n, dtype=synth.RESULT_DTYPE)
+    ev = None if evalue is None else np.ascontiguousarray(evalue, np.float64)
+    un = None if unclassified is None else np.ascontiguousarray(unclassified, np.uint8)
+    for s in range(n):
+        b, c = int(segs[s]["cand_begin"]), int(segs[s]["cand_count"])
+        cc = np.ascontiguousarray(cands[b:b + c])
+        evs = None if ev is None else np.ascontiguousarray(ev[b:b + c])
+        rc = f(ptr(parent, u32p), ptr(left, u32p), ptr(right, u32p), ptr(depth, u8p), ctypes.c_uint32(len(parent)),
+               ctypes.c_uint32(0), ctypes.c_uint32(int(model)), ctypes.c_float(toppercent), ctypes.c_float(minscore),
+               ctypes.c_double(maxevalue), ctypes.c_uint32(int(minsupport)), ctypes.c_uint32(int(nbest)),
+               ctypes.c_int(int(bool(ignore_unclassified))), cc.ctypes.data_as(ctypes.c_void_p),
+               None if evs is None else evs.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(c),
+               None if un is None else un.ctypes.data_as(ctypes.c_void_p), res[s:s + 1].ctypes.data_as(ctypes.c_void_p))
+        assert rc == 0
+    return res

@@ -1,0 +1,110 @@
+"""The alignment-free placement models (simple-lca, megan-lca / ic-megan-lca, n-best-lca, dummy;
+core/src/taxonpredictionmodel.hh:57-259) -- SURVEY.md 8 f4.
+CPU: the oracle restatement reproduces the GFF3 of the REAL reference binary (tests/golden/lca_*.gff3, generated
+by tests/golden/make_golden_lca.py).  GPU: trpa_predict_lca_batch equals the oracle on the golden cases and on
+adversarial random tables, and the drop-in CLI reproduces the reference's files byte for byte."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+import oracle_lib as ol
+import synth
+
+LCA_FIELDS = ["qrstart", "qrstop", "lower_node", "upper_node", "rtax_node", "support", "kind", "ival"]
+
+
+def _render(d, parent, depth, segs, res):
+    import gff3
+    q_len = np.array([len(s) for s in d.q_seqs], np.uint32)
+    return sorted(gff3.render(res, segs, d.q_names, q_len, parent, depth, [str(t) for t in d.tax_ids]))
+
+
+def _case(case):
+    d, evalue, named = gu.lca_case_data(case)
+    parent, left, right, depth = d.nested_set()
+    segs, cands, ev = gu.lca_flat(d, evalue)
+    uncl = gu.lca_unclassified_flags(d, named)
+    return d, (parent, left, right, depth), segs, cands, ev, uncl
+
+
+@pytest.mark.parametrize("case", gu.LCA_CASES)
+def test_oracle_matches_reference_gff3(case):
+    d, tax, segs, cands, ev, uncl = _case(case)
+    for variant, (_, kw) in gu.LCA_VARIANTS.items():
+        res = ol.oracle_predict_lca(*tax, segs, cands, ev, uncl, **kw)
+        assert _render(d, tax[0], tax[3], segs, res) == gu.lca_golden_lines(case, variant), variant
+
+
+def _random_tables(rng, n_nodes, n_segs):
+    """Adversarial record sets: ties, reversed query ranges, empty and > 32-record sets, scores below / above 0."""
+    counts = rng.choice([0, 1, 2, 3, 7, 31, 32, 33, 64, 65, 150], n_segs)
+    n = int(counts.sum())
+    cands = np.zeros(n, synth.CAND_DTYPE)
+    cands["score"] = rng.choice(np.array([-8, 0, 8, 16, 40, 40, 48, 56, 120, 128, 500], np.float32), n)
+    a = rng.integers(1, 5000, n); b = rng.integers(1, 5000, n)
+    cands["qstart"], cands["qstop"] = a, b            # either orientation
+    cands["node"] = rng.integers(0, n_nodes, n)
+    ev = np.power(10.0, -rng.integers(-4, 30, n).astype(np.float64))
+    segs = np.zeros(n_segs, synth.SEG_DTYPE)
+    segs["cand_count"] = counts
+    segs["cand_begin"] = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    return segs, cands, ev
+
+
+PARAM_SETS = [dict(model=0), dict(model=1), dict(model=2), dict(model=2, toppercent=1.0, minsupport=1),
+              dict(model=2, toppercent=0.3, minscore=16.0, maxevalue=1e-3, minsupport=2),
+              dict(model=2, toppercent=0.0, minscore=-100.0, maxevalue=1e-20, minsupport=1, ignore_unclassified=True),
+              dict(model=2, toppercent=0.5, minsupport=4, ignore_unclassified=True),
+              dict(model=3, nbest=0), dict(model=3, nbest=1), dict(model=3, nbest=2), dict(model=3, nbest=50)]
+
+
+@pytest.mark.gpu
+def test_gpu_equals_oracle_random(ctx):
+    d, tax, _, _, _, uncl = _case("nt_small")
+    ctx.load_taxonomy(*tax, 0)
+    rng = np.random.default_rng(77)
+    segs, cands, ev = _random_tables(rng, len(tax[0]), 400)
+    for kw in PARAM_SETS:
+        for use_ev, use_un in ((True, True), (False, False)):
+            want = ol.oracle_predict_lca(*tax, segs, cands, ev if use_ev else None, uncl if use_un else None, **kw)
+            got, _ = ctx.predict_lca_batch(kw["model"], segs, cands, ev if use_ev else None, uncl if use_un else None,
+                                           **{k: v for k, v in kw.items() if k != "model"})
+            bad = ol.results_equal(got, want, LCA_FIELDS)
+            assert not bad, (kw, use_ev, bad)
+    # empty batch, bad node
+    assert len(ctx.predict_lca_batch(1, segs[:0], cands[:0])[0]) == 0
+    import rpa_b200
+    bad = cands.copy(); bad["node"][3] = 10 ** 6
+    with pytest.raises(rpa_b200.TrpaError):
+        ctx.predict_lca_batch(1, segs, bad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", gu.LCA_CASES)
+def test_gpu_matches_reference_gff3(ctx, case):
+    d, tax, segs, cands, ev, uncl = _case(case)
+    ctx.load_taxonomy(*tax, 0)
+    for variant, (_, kw) in gu.LCA_VARIANTS.items():
+        got, _ = ctx.predict_lca_batch(kw["model"], segs, cands, ev, uncl, **{k: v for k, v in kw.items() if k != "model"})
+        assert _render(d, tax[0], tax[3], segs, got) == gu.lca_golden_lines(case, variant), variant
+
+
+@pytest.mark.gpu
+def test_cli_matches_reference_gff3(tmp_path):
+    exe = os.path.join(ol.ROOT, "taxator-tk_b200", "bin", "taxator-b200")
+    assert os.path.exists(exe), "build first: make -C taxator-tk_b200"
+    case = "nt_small"
+    d, evalue, named = gu.lca_case_data(case)
+    tmp = str(tmp_path / case)
+    gu.lca_write_files(d, evalue, named, tmp)
+    env = dict(os.environ, TAXATORTK_TAXONOMY_NCBI=tmp)
+    for variant, (args, _) in gu.LCA_VARIANTS.items():
+        with open(os.path.join(tmp, "alignments.tsv"), "rb") as fin:
+            out = subprocess.run([exe] + args + ["-g", "mapping.tax", "-p", "1", "-o", "0", "--batch-segments", "50"], cwd=tmp,
+                                 env=env, stdin=fin, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout.decode()
+        assert out.startswith("##gff-version 3\n")
+        lines = sorted(l + "\n" for l in out.splitlines() if not l.startswith("##"))
+        assert lines == gu.lca_golden_lines(case, variant), variant

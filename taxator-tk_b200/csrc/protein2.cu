@@ -95,34 +95,48 @@ __device__ __forceinline__ int protein2_strip(const uint8_t* __restrict__ a, con
     const int j = s0 + v + 1;
     diag0 = (v >= 0) ? p2_boundary(j) : p2_boundary(s0);
   }
-  int last = 0, res = 0;
-  const int steps = m + 31;
-  for (int t = 1; t <= steps; ++t) {
-    const int recv = __shfl_up_sync(0xffffffffu, last, 1);
-    const int i = t - (int)lane;
-    if (i >= 1 && i <= m) {
-      int left;
-      if (lane == 0) left = first_strip ? (p2_boundary(i) + i * ROWBIAS) : my_scratch[i];
-      else left = recv;
-      const int left_in = left;
-      int diag = diag0;
-      const unsigned char* prow = prof + (int)b[i - 1] * (CQ * 128);
+  // TWO rows per wavefront step: lane l works on rows 2(t-l)-1 and 2(t-l) at step t.  Both row bodies are
+  // straight-line code in one basic block, so the scheduler interleaves row i+1's first cells with row i's
+  // last ones (two independent max chains instead of one: the fixed-latency "wait" stall was the largest,
+  // profiles/r02_protein2_ncu.md) and the per-step bookkeeping (shuffles, predicates, addresses) is paid
+  // once per two rows.  A row past the end (m odd) is computed on clamped inputs and never read.
+  int last0 = 0, last1 = 0, res = 0;
+  const int steps = ((m + 1) >> 1) + 31;
+  auto row = [&](const unsigned char* prow, int left, int diag) -> int {
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const int e = prow[(c >> 2) * 128 + (c & 3)];
-        const int D = e * (1 << (SH - 1)) + diag;   // score + sub, priority 2, gaps unchanged, row bias + 1
-        const int V = up[c] + CV;
-        const int H = left + CH;
-        const int cell = max3i(D, V, H) & ~PRIO_MASK;
-        diag = up[c];
-        up[c] = cell;
-        left = cell;
-      }
-      diag0 = left_in;
-      last = left;
+    for (int c = 0; c < C; ++c) {
+      const int e = prow[(c >> 2) * 128 + (c & 3)];
+      const int D = e * (1 << (SH - 1)) + diag;   // score + sub, priority 2, gaps unchanged, row bias + 1
+      const int V = up[c] + CV;
+      const int H = left + CH;
+      const int cell = max3i(D, V, H) & ~PRIO_MASK;
+      diag = up[c];
+      up[c] = cell;
+      left = cell;
+    }
+    return left;
+  };
+  for (int t = 1; t <= steps; ++t) {
+    const int recv0 = __shfl_up_sync(0xffffffffu, last0, 1);
+    const int recv1 = __shfl_up_sync(0xffffffffu, last1, 1);
+    const int i0 = 2 * (t - (int)lane) - 1, i1 = i0 + 1;
+    if (i0 >= 1 && i0 <= m) {
+      int left0, left1;
+      if (lane == 0) {
+        const int j1 = i1 <= m ? i1 : m;
+        left0 = first_strip ? (p2_boundary(i0) + i0 * ROWBIAS) : my_scratch[i0];
+        left1 = first_strip ? (p2_boundary(i1) + i1 * ROWBIAS) : my_scratch[j1];
+      } else { left0 = recv0; left1 = recv1; }
+      const unsigned char* prow0 = prof + (int)b[i0 - 1] * (CQ * 128);
+      const unsigned char* prow1 = prof + (int)b[(i1 <= m ? i1 : m) - 1] * (CQ * 128);
+      const int l0 = row(prow0, left0, diag0);      // row i0: diagonal input = left boundary of row i0 - 1
+      const int l1 = row(prow1, left1, left0);      // row i1: diagonal input = left boundary of row i0
+      diag0 = left1;
+      last0 = l0; last1 = l1;
       if (lane == 31) {
-        if (!last_strip) my_scratch[i] = left;
-        else if (i == m) res = left;
+        if (!last_strip) { my_scratch[i0] = l0; if (i1 <= m) my_scratch[i1] = l1; }
+        else if (i0 == m) res = l0;
+        else if (i1 == m) res = l1;
       }
     }
   }

@@ -94,6 +94,7 @@ cudaError_t launch_myers(int shape, const PairDesc* pairs, u32 count, const SeqD
 __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const SeqDesc* __restrict__ descs,
                             const uint2* __restrict__ planes, const u32* __restrict__ nplane,
                             u32* __restrict__ hist, u32 lanes_total, int band, int force_shape, int wedge, const PlanParams pp) {
+  __shared__ u32 plan_bins[4][32];   // blockDim.x == 128
   const u32 lane = threadIdx.x & 31;
   const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -106,18 +107,25 @@ __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const Seq
     const int hasn = (int)((A.flags | B.flags) & 1u);
     u32 k0 = kPadKFull, a1 = 0;
     if (band && m >= 64u) {
-      // every lane counts the mismatches of one contiguous 1/32 of the pattern, so that the prefix sums
-      // over the lanes give the mismatch profile along the sequence
+      // lane l ends up with the mismatches of the l-th contiguous 1/32 of the pattern, so that the prefix sums
+      // over the lanes give the mismatch profile along the sequence.  The words are READ interleaved
+      // (coalesced) and binned through a 32-entry shared-memory histogram per warp.
       const u32 mwords = (m + 31) >> 5;
       const u32 per = (mwords + 31u) >> 5;
-      u32 h = 0;
-      for (u32 w = lane * per; w < (lane + 1u) * per && w < mwords; ++w) {
+      u32* bins = plan_bins[threadIdx.x >> 5];
+      bins[lane] = 0u;
+      __syncwarp();
+      for (u32 w = lane; w < mwords; w += 32u) {
         const uint2 x = planes[pw + w], y = planes[tw + w];
         u32 mm = (x.x ^ y.x) | (x.y ^ y.y);
         if (hasn) mm |= nplane[pw + w] ^ nplane[tw + w];
         if (w == mwords - 1 && (m & 31u)) mm &= (1u << (m & 31u)) - 1u;
-        h += __popc(mm);
+        const u32 c = __popc(mm);
+        if (c) atomicAdd(&bins[w / per], c);
       }
+      __syncwarp();
+      const u32 h = bins[lane];
+      __syncwarp();
       u32 cum = h;   // inclusive prefix sum over the lanes
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {

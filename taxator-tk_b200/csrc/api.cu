@@ -152,6 +152,8 @@ struct trpa_ctx {
   DevBuf<StageReq> d_stage;
   DevBuf<uint2> arena_planes;
   DevBuf<uint2> arena_codes;     // column codes of the staged words (common.cuh nt_codes)
+  // tables of trpa_predict_lca_batch (kept between calls: no allocation in the steady state)
+  DevBuf<trpa_segment> l_segs; DevBuf<trpa_candidate> l_cands; DevBuf<double> l_ev; DevBuf<uint8_t> l_un; DevBuf<trpa_result> l_out;
   DevBuf<u32> arena_n;
   DevBuf<uint8_t> arena_aa;
   u64 arena_units = 0;
@@ -508,7 +510,8 @@ void trpa_destroy(trpa_ctx* c) {
   c->d_qd.release(); c->d_qsim.release(); c->d_bf_d.release(); c->d_cflags.release(); c->d_og_i.release(); c->d_tag.release();
   c->d_bf_node.release(); c->d_og_d.release(); c->d_res.release(); c->d_descs.release(); c->d_pairs.release();
   c->d_pairs_sorted.release(); c->d_stage.release();
-  c->arena_planes.release(); c->arena_codes.release(); c->arena_n.release(); c->arena_aa.release();
+  c->arena_planes.release(); c->arena_codes.release(); c->arena_n.release();
+  c->l_segs.release(); c->l_cands.release(); c->l_ev.release(); c->l_un.release(); c->l_out.release(); c->arena_aa.release();
   for (int i = trpa_ctx::kMaxPipes - 1; i >= 0; --i) c->pipe[i].release();
   delete c;
 }
@@ -1254,7 +1257,8 @@ int trpa_predict_lca_batch(trpa_ctx* c, const trpa_lca_params* pp, const trpa_se
   }
   for (u32 i = 0; i < n_cands; ++i)
     if (cands[i].node >= c->n_nodes) { set_error("candidate node out of range"); return TRPA_ERR_ARG; }
-  DevBuf<trpa_segment> d_segs; DevBuf<trpa_candidate> d_cands; DevBuf<double> d_ev; DevBuf<uint8_t> d_un; DevBuf<trpa_result> d_out;
+  DevBuf<trpa_segment>& d_segs = c->l_segs; DevBuf<trpa_candidate>& d_cands = c->l_cands; DevBuf<double>& d_ev = c->l_ev;
+  DevBuf<uint8_t>& d_un = c->l_un; DevBuf<trpa_result>& d_out = c->l_out;
   if (d_segs.ensure(n_segs) || d_cands.ensure(n_cands + 1) || d_out.ensure(n_segs) || (evalue && d_ev.ensure(n_cands + 1)) ||
       (node_unclassified && d_un.ensure(c->n_nodes)))
     return TRPA_ERR_NOMEM;
@@ -1279,7 +1283,6 @@ int trpa_predict_lca_batch(trpa_ctx* c, const trpa_lca_params* pp, const trpa_se
   if (kernel_ms) *kernel_ms = ms / repeat;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   c->prof.launches_other += (u64)repeat;
-  d_segs.release(); d_cands.release(); d_ev.release(); d_un.release(); d_out.release();
   return 0;
 }
 

@@ -146,7 +146,6 @@ TRPA_HD BandGeom band_from_k(uint32_t m, uint32_t n, uint32_t k, bool force_full
 // Group steps the rotating schedule needs for one attempt (long schedules are sampled: the gap is
 // piecewise linear in the round index).
 TRPA_HD uint64_t band_steps(const BandGeom& g, int W, int L) {
-  const uint32_t R = 32u * (uint32_t)W;
   const uint32_t mwords = (g.m + 31u) >> 5, nblk = (g.n + 31u) >> 5;
   const uint32_t S = (mwords + W - 1) / W;
   uint64_t off = 0;

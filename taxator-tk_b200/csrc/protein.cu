@@ -120,7 +120,7 @@ protein_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __r
 }
 
 cudaError_t launch_protein2(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,
-                            int2* out2, int2* scratch, u32 scratch_stride, cudaStream_t stream);
+                            int2* out2, int2* scratch, u32 scratch_stride, u32 max_len, cudaStream_t stream);
 int protein2_max_len();
 
 static bool protein_v1_only() {
@@ -140,7 +140,7 @@ cudaError_t launch_protein(const PairDesc* pairs, u32 count, const SeqDesc* seqs
     protein_kernel<<<blocks, 128, 0, stream>>>(pairs, count, seqs, residues, out2, scratch, scratch_stride, -1);
     return cudaGetLastError();
   }
-  e = launch_protein2(pairs, count, seqs, residues, out2, scratch, scratch_stride, stream);
+  e = launch_protein2(pairs, count, seqs, residues, out2, scratch, scratch_stride, max_len, stream);
   if (e != cudaSuccess) return e;
   if ((int)max_len > protein2_max_len()) {
     protein_kernel<<<blocks, 128, 0, stream>>>(pairs, count, seqs, residues, out2, scratch, scratch_stride, protein2_max_len());

@@ -101,11 +101,15 @@ __device__ __forceinline__ int protein2_strip(const uint8_t* __restrict__ a, con
   // profiles/r02_protein2_ncu.md) and the per-step bookkeeping (shuffles, predicates, addresses) is paid
   // once per two rows.  A row past the end (m odd) is computed on clamped inputs and never read.
   int last0 = 0, last1 = 0, res = 0;
+  const u32 prof_sa = (u32)__cvta_generic_to_shared(prof);
   const int steps = ((m + 1) >> 1) + 31;
-  auto row = [&](const unsigned char* prow, int left, int diag) -> int {
+  // one LDS.U8 per cell (bank == lane, conflict free): the LSU pipe has room, the alu pipe does not -- a 32-bit
+  // load per four cells costs a PRMT byte extract per cell on the alu pipe
+  auto row = [&](u32 prow, int left, int diag) -> int {
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const int e = prow[(c >> 2) * 128 + (c & 3)];
+      int e;
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(e) : "r"(prow + (u32)((c >> 2) * 128 + (c & 3))));   // ptxas folds the offset
       const int D = e * (1 << (SH - 1)) + diag;   // score + sub, priority 2, gaps unchanged, row bias + 1
       const int V = up[c] + CV;
       const int H = left + CH;
@@ -127,8 +131,8 @@ __device__ __forceinline__ int protein2_strip(const uint8_t* __restrict__ a, con
         left0 = first_strip ? (p2_boundary(i0) + i0 * ROWBIAS) : my_scratch[i0];
         left1 = first_strip ? (p2_boundary(i1) + i1 * ROWBIAS) : my_scratch[j1];
       } else { left0 = recv0; left1 = recv1; }
-      const unsigned char* prow0 = prof + (int)b[i0 - 1] * (CQ * 128);
-      const unsigned char* prow1 = prof + (int)b[(i1 <= m ? i1 : m) - 1] * (CQ * 128);
+      const u32 prow0 = prof_sa + (u32)b[i0 - 1] * (u32)(CQ * 128);
+      const u32 prow1 = prof_sa + (u32)b[(i1 <= m ? i1 : m) - 1] * (u32)(CQ * 128);
       const int l0 = row(prow0, left0, diag0);      // row i0: diagonal input = left boundary of row i0 - 1
       const int l1 = row(prow1, left1, left0);      // row i1: diagonal input = left boundary of row i0
       diag0 = left1;
@@ -147,9 +151,11 @@ __device__ __forceinline__ int protein2_strip(const uint8_t* __restrict__ a, con
 __global__ void __launch_bounds__(128)
 protein2_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __restrict__ seqs,
                 const uint8_t* __restrict__ residues, int2* __restrict__ out2, int2* __restrict__ scratch,
-                u32 scratch_stride) {
+                u32 scratch_stride, u32 cq_rt) {
+  // cq_rt: column quads per lane the shared-memory profile is sized for (the launch's longest sequence decides:
+  // 300-aa batches need 3 instead of 4 quads and fit a fifth CTA per SM)
   extern __shared__ __align__(16) signed char prof_all[];
-  signed char* tbl = prof_all + kP2ProfBytes;   // BLOSUM62 [a][b]
+  signed char* tbl = prof_all + (size_t)kP2Warps * 27 * cq_rt * 128;   // BLOSUM62 [a][b]
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) tbl[i] = c_blosum_p2[i >> 5][i & 31];
   __syncthreads();
   const u32 lane = threadIdx.x & 31;
@@ -167,12 +173,13 @@ protein2_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __
     if (lane == 0) out2[pd.out] = make_int2(-(n + m), 0);
     return;
   }
-  unsigned char* prof = reinterpret_cast<unsigned char*>(prof_all) + ((size_t)warp_in_cta * 27 * kCQ * 32 + lane) * 4;  // [b][c/4][lane][c%4]
+  unsigned char* prof = reinterpret_cast<unsigned char*>(prof_all) + ((size_t)warp_in_cta * 27 * cq_rt * 32 + lane) * 4;  // [b][c/4][lane][c%4]
   int* my_scratch = reinterpret_cast<int*>(scratch + (size_t)warp_gid * scratch_stride);
   int res = 0;
   int ns = ((n - 1) % (32 * kC2Max)) + 1;  // the first strip takes the remainder, later strips are full
   for (int s0 = 0; s0 < n; s0 += ns, ns = 32 * kC2Max) {
     const int Cneed = (ns + 31) >> 5;
+    if (Cneed > 4 * (int)cq_rt) __trap();   // the launcher sized the profile from a wrong max_len: fail loudly
     const bool first = s0 == 0, lastS = s0 + ns == n;
     if (Cneed <= 4) res = protein2_strip<4>(a, b, m, s0, ns, first, lastS, prof, tbl, my_scratch, lane);
     else if (Cneed <= 8) res = protein2_strip<8>(a, b, m, s0, ns, first, lastS, prof, tbl, my_scratch, lane);
@@ -190,7 +197,7 @@ protein2_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __
 }
 
 cudaError_t launch_protein2(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,
-                            int2* out2, int2* scratch, u32 scratch_stride, cudaStream_t stream) {
+                            int2* out2, int2* scratch, u32 scratch_stride, u32 max_len, cudaStream_t stream) {
   if (count == 0) return cudaSuccess;
   cudaError_t e = ensure_table2();
   if (e != cudaSuccess) return e;
@@ -201,7 +208,14 @@ cudaError_t launch_protein2(const PairDesc* pairs, u32 count, const SeqDesc* seq
     attr = true;
   }
   const u32 blocks = (count + kP2Warps - 1) / kP2Warps;
-  protein2_kernel<<<blocks, 32 * kP2Warps, kP2SmemBytes, stream>>>(pairs, count, seqs, residues, out2, scratch, scratch_stride);
+  // profile capacity: columns per lane of the longest strip any pair of this launch can have
+  const u32 longest = max_len ? (max_len > (u32)kP2MaxLen ? (u32)kP2MaxLen : max_len) : (u32)kP2MaxLen;
+  u32 cols = (longest + 31u) / 32u;
+  if (cols > (u32)kC2Max) cols = kC2Max;
+  // the strip templates round the columns per lane up to 4, 8, 10, 12 or 16
+  const u32 cq = cols <= 4 ? 1u : (cols <= 8 ? 2u : (cols <= 12 ? 3u : 4u));
+  const size_t smem = (size_t)kP2Warps * 27 * cq * 128 + 27 * 32;
+  protein2_kernel<<<blocks, 32 * kP2Warps, smem, stream>>>(pairs, count, seqs, residues, out2, scratch, scratch_stride, cq);
   return cudaGetLastError();
 }
 

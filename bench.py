@@ -61,9 +61,12 @@ WORKLOADS = {
                           levels=(2, 4, 6, 10, 20)), cpu_sample=200),
 }
 
-# ALU-pipe instructions per 32-cell word-step of the W=20 edit-distance kernel, counted in SASS
-# (profiles/r01_sass_mix.md, myers2_column<W> shared by myers2/myers3): 7.1 LOP3 + 2.2 SHF + 1.03 IADD3.X + 0.1 other.
-ALU_OPS_PER_WORDSTEP = 10.4
+# ALU-pipe instructions per 32-cell word-step: the MINIMUM of the bit-vector formulation (7 LOP3 + 2 SHF +
+# 1 IADD3.X, myers3_column); what the column loop really issues is 10.9 at W = 4 and 10.2 at W = 20
+# (scripts/sass_loop.py).  Rounds r01-r02 quoted the roofline on the 10.4 counted for the W = 20 kernel of r01
+# (profiles/r01_sass_mix.md); that figure is still reported as frac_r01_constant.
+ALU_OPS_PER_WORDSTEP = 10.0
+ALU_OPS_PER_WORDSTEP_R01 = 10.4
 
 
 def make_data(workload, seed, n_queries=None):
@@ -483,6 +486,8 @@ def main():
                 "peak_source": "own probe trpa_int_alu_peak (%.3e lane-ops/s) / %.1f ALU ops per 32-cell word-step"
                                % (alu_peak, ALU_OPS_PER_WORDSTEP) if not fd.protein else "own probe trpa_int_alu_peak / 3 alu ops per cell",
                 "kernel_ms_per_step": k_ms / args.steps, "kernel_share_of_step": (k_ms / args.steps) / ms_step}
+    if not fd.protein and peak:
+        roofline["frac_r01_constant"] = roofline["frac"] * ALU_OPS_PER_WORDSTEP_R01 / ALU_OPS_PER_WORDSTEP
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

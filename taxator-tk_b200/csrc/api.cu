@@ -169,7 +169,7 @@ struct trpa_ctx {
   u32 la_max = 32;            // largest automatic look-ahead budget per segment and round
   int force_shape = -1;       // tuning hook: (lidx * kNumW + widx) forced for every pair, -1 = planner
   PlanParams plan;            // hint margin + cost model of the shape planner (tuning hooks)
-  u32 plan_lanes = 0;         // test hook: lanes the shape planner assumes (0 = num_sms * 16 warps * 32)
+  u32 plan_lanes = 0;         // tuning hook: weight of a pair's latency against the summed lane-time in the shape planner (0 = num_sms * 48 warps * 32: measured, 2-8 x the resident lanes all give C4 +7..9 %, C5 +5 %, C2 -1 %)
   int num_sms = 148;
   // profiling
   trpa_profile prof;
@@ -370,7 +370,7 @@ static int bucket_pairs3(trpa_ctx* c, Pipe& P, PairDesc* pairs, u32 n_pairs, con
                          const u32* nplane, PairDesc* sorted, u32* h_hist) {
   CK(cudaMemsetAsync(P.d_hist.p, 0, sizeof(u32) * 3 * kNumShapes, P.stream));
   const u32 blocks = std::min<u32>((n_pairs + 255) / 256, 148 * 8);
-  CK(launch_plan(pairs, n_pairs, descs, planes, nplane, P.d_hist.p, c->plan_lanes ? c->plan_lanes : (u32)c->num_sms * 16u * 32u,
+  CK(launch_plan(pairs, n_pairs, descs, planes, nplane, P.d_hist.p, c->plan_lanes ? c->plan_lanes : (u32)c->num_sms * 48u * 32u,
                  c->band ? (c->band_k0 ? (int)c->band_k0 : 1) : 0, c->force_shape, c->wedge, c->plan, P.stream));
   scan_kernel<<<1, 32, 0, P.stream>>>(P.d_hist.p, P.d_buckets.p);
   scatter_kernel<<<blocks, 256, 0, P.stream>>>(pairs, n_pairs, P.d_hist.p, sorted);

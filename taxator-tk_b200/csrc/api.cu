@@ -91,7 +91,8 @@ struct Pipe {
   bool own_stream = false;
   bool ready = false;
   DevBuf<u32> d_counters;
-  DevBuf<u32> d_hist;         // kNumShapes counts + scatter cursors + kernel work cursors
+  DevBuf<u32> d_hist;         // kNumShapes counts + scatter cursors + kernel work cursors, then (banded path)
+                              // kNumShapes x kNumCls duration-class counts and their scatter cursors
   DevBuf<uint2> d_buckets;    // kNumShapes {start,count}
   DevBuf<u32> scratch;
   DevBuf<uint4> scratch3;     // banded kernel: wrap-around strip boundaries, one line per group slot
@@ -169,7 +170,7 @@ struct trpa_ctx {
   u32 la_max = 32;            // largest automatic look-ahead budget per segment and round
   int force_shape = -1;       // tuning hook: (lidx * kNumW + widx) forced for every pair, -1 = planner
   PlanParams plan;            // hint margin + cost model of the shape planner (tuning hooks)
-  u32 plan_lanes = 0;         // tuning hook: weight of a pair's latency against the summed lane-time in the shape planner (0 = num_sms * 48 warps * 32: measured, 2-8 x the resident lanes all give C4 +7..9 %, C5 +5 %, C2 -1 %)
+  u32 plan_lanes = 0;         // tuning hook: weight of a pair's latency against the summed lane-time in the shape planner (0 = automatic, see bucket_pairs3)
   int num_sms = 148;
   // profiling
   trpa_profile prof;
@@ -212,6 +213,33 @@ __global__ void scan_kernel(u32* hist, uint2* buckets) {
       hist[kNumShapes + s] = acc;  // scatter cursor
       acc += c;
     }
+  }
+}
+// banded path: buckets by shape and, inside a shape, by duration class, longest first (the persistent groups pull
+// pairs in this order: longest-processing-time-first keeps the tail of a launch short)
+constexpr u32 kHistWords = 3u * kNumShapes + 2u * kNumShapes * kNumCls;
+__global__ void scan3_kernel(u32* hist, uint2* buckets) {
+  __shared__ u32 start[kNumShapes];
+  const int s = threadIdx.x;
+  if (s == 0) {
+    u32 acc = 0;
+    for (int i = 0; i < kNumShapes; ++i) { start[i] = acc; buckets[i] = make_uint2(acc, hist[i]); acc += hist[i]; }
+  }
+  __syncthreads();
+  if (s < kNumShapes) {
+    const u32* cnt = hist + 3 * kNumShapes + s * kNumCls;
+    u32* cur = hist + 3 * kNumShapes + kNumShapes * kNumCls + s * kNumCls;
+    u32 acc = start[s];
+    for (int c = kNumCls - 1; c >= 0; --c) { cur[c] = acc; acc += cnt[c]; }
+  }
+}
+__global__ void scatter3_kernel(const PairDesc* pairs, u32 n, u32* hist, PairDesc* sorted) {
+  u32* cur = hist + 3 * kNumShapes + kNumShapes * kNumCls;
+  for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const PairDesc p = pairs[k];
+    const u32 cls = p.cls < (u32)kNumCls ? p.cls : (u32)kNumCls - 1u;
+    const u32 pos = atomicAdd(&cur[(p.pad & 0xffu) * kNumCls + cls], 1u);   // pad: shape | k0 << 8
+    sorted[pos] = p;
   }
 }
 __global__ void scatter_kernel(const PairDesc* pairs, u32 n, u32* hist, PairDesc* sorted) {
@@ -296,7 +324,7 @@ int Pipe::init(cudaStream_t user_stream) {
     own_stream = true;
   }
   CK(cudaMallocHost(&h_counters, sizeof(u32) * (kNumCounters + 2 * kNumShapes)));
-  if (d_counters.ensure(kNumCounters) || d_hist.ensure(3 * kNumShapes) || d_buckets.ensure(kNumShapes) || d_plan.ensure(8)) return TRPA_ERR_NOMEM;
+  if (d_counters.ensure(kNumCounters) || d_hist.ensure(kHistWords) || d_buckets.ensure(kNumShapes) || d_plan.ensure(8)) return TRPA_ERR_NOMEM;
   CK(cudaMemsetAsync(d_plan.p, 0, 8 * sizeof(unsigned long long), stream));
   CK(cudaStreamSynchronize(stream));
   ready = true;
@@ -368,12 +396,15 @@ static int launch_myers_shapes(trpa_ctx* c, Pipe& P, const u32* h_hist, const Pa
 // ---- banded path: plan (threshold + shape per pair), counting sort by shape, one launch per shape
 static int bucket_pairs3(trpa_ctx* c, Pipe& P, PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, const uint2* planes,
                          const u32* nplane, PairDesc* sorted, u32* h_hist) {
-  CK(cudaMemsetAsync(P.d_hist.p, 0, sizeof(u32) * 3 * kNumShapes, P.stream));
+  CK(cudaMemsetAsync(P.d_hist.p, 0, sizeof(u32) * kHistWords, P.stream));
   const u32 blocks = std::min<u32>((n_pairs + 255) / 256, 148 * 8);
-  CK(launch_plan(pairs, n_pairs, descs, planes, nplane, P.d_hist.p, c->plan_lanes ? c->plan_lanes : (u32)c->num_sms * 48u * 32u,
+  // weight of a pair's own latency against the summed lane-time = the resident lanes; the planner makes the latency
+  // term convex (long pairs are the tail of a round, see plan_kernel)
+  const u32 lat_weight = c->plan_lanes ? c->plan_lanes : (u32)c->num_sms * 16u * 32u;
+  CK(launch_plan(pairs, n_pairs, descs, planes, nplane, P.d_hist.p, lat_weight,
                  c->band ? (c->band_k0 ? (int)c->band_k0 : 1) : 0, c->force_shape, c->wedge, c->plan, P.stream));
-  scan_kernel<<<1, 32, 0, P.stream>>>(P.d_hist.p, P.d_buckets.p);
-  scatter_kernel<<<blocks, 256, 0, P.stream>>>(pairs, n_pairs, P.d_hist.p, sorted);
+  scan3_kernel<<<1, 128, 0, P.stream>>>(P.d_hist.p, P.d_buckets.p);
+  scatter3_kernel<<<blocks, 256, 0, P.stream>>>(pairs, n_pairs, P.d_hist.p, sorted);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(h_hist, P.d_hist.p, sizeof(u32) * kNumShapes, cudaMemcpyDeviceToHost, P.stream));
   return 0;   // asynchronous: synchronise P.stream before reading h_hist
@@ -541,6 +572,7 @@ int trpa_set_tuning(trpa_ctx* c, const char* key, int64_t value) {
   const std::string k(key);
   if (k == "band_k0") c->band_k0 = value < 0 ? 0u : (u32)std::min<int64_t>(value, 0xfffffe);
   else if (k == "hint_mul64") c->plan.hint_mul64 = (u32)std::max<int64_t>(1, std::min<int64_t>(value, 1 << 16));
+  else if (k == "tail_log2") c->plan.tail_log2 = (u32)std::max<int64_t>(9, std::min<int64_t>(value, 40));
   else if (k == "hint_add") c->plan.hint_add = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
   else if (k == "cost_word10") c->plan.word10 = (u32)std::max<int64_t>(1, std::min<int64_t>(value, 1 << 16));
   else if (k == "cost_col10") c->plan.col10 = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 16));

@@ -180,7 +180,7 @@ __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const Seq
       }
     }
     const BandGeom g = band_from_k(m ? m : 1u, n ? n : 1u, k0 >= kPadKFull ? 0xffffffffu : k0, !band, a1);
-    uint64_t key = ~0ull;
+    uint64_t key = ~0ull, mytime = 0;
     int best = 0;
     // 32 candidates, one per lane: W in {2, 4, 8, 12, 16} x L in {1 .. 32}, + W in {20, 24} at L = 32
     // (long patterns with wide bands); W = 1 never wins (per-column overhead)
@@ -189,21 +189,30 @@ __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const Seq
       if (lane < 30) { w = 1 + (int)(lane % 5u); l = (int)(lane / 5u); }
       else { w = 6 + (int)(lane - 30u); l = kNumL - 1; }
       const ShapeCost sc = band_shape_cost(g, w, l, pp);
-      key = sc.cost * n_pairs + sc.time * lanes_total;
+      // lane-time when pairs are plentiful, latency when they are scarce; the latency term is convex (time +
+      // time^2 / 2^pp.tail_log2): a pair that runs for a large part of a round IS the round's tail, short pairs hide
+      // behind the others (measured with the longest-first bucket order)
+      const uint64_t t2 = (sc.time >> 8) * (sc.time >> (pp.tail_log2 - 8u));
+      key = sc.cost * n_pairs + (sc.time + t2) * lanes_total;
       best = l * kNumW + w;
+      mytime = sc.time;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const uint64_t ok = __shfl_xor_sync(0xffffffffu, key, o);
       const int ob = __shfl_xor_sync(0xffffffffu, best, o);
-      if (ok < key || (ok == key && ob < best)) { key = ok; best = ob; }
+      const uint64_t ot = __shfl_xor_sync(0xffffffffu, mytime, o);
+      if (ok < key || (ok == key && ob < best)) { key = ok; best = ob; mytime = ot; }
     }
     if (force_shape >= 0) best = force_shape;
     if (lane == 0) {
       const int shape = shape_id(best % kNumW, best / kNumW, hasn);
       pairs[p].pad = (k0 << 8) | (u32)shape;
       pairs[p].aux = g.wedge() ? a1 : 0u;
+      const u32 cls = duration_class(mytime);
+      pairs[p].cls = cls;
       atomicAdd(&hist[shape], 1u);
+      atomicAdd(&hist[3 * kNumShapes + shape * kNumCls + cls], 1u);
     }
   }
 }

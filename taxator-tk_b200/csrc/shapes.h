@@ -166,10 +166,19 @@ TRPA_HD uint64_t band_steps(const BandGeom& g, int W, int L) {
 //  column) + step (boundary hand-over, schedule); strip set-up (equality table, geometry): setup + setup_w * W
 struct PlanParams {
   uint32_t hint_mul64 = 72, hint_add = 32;
+  uint32_t tail_log2 = 22;   // latency penalty time + time^2 / 2^tail_log2 (>= 9)
   uint32_t word10 = 100, col10 = 35, step = 200, setup = 250, setup_w = 25;   // SASS + ncu region counts, profiles/r03_myers3_ncu.md
 };
 TRPA_HD uint64_t band_step_ops(int W, const PlanParams& pp) { return 32ull * ((uint64_t)pp.word10 * (uint64_t)W + pp.col10) / 10ull + pp.step; }
 TRPA_HD uint64_t band_setup_ops(int W, const PlanParams& pp) { return pp.setup + (uint64_t)pp.setup_w * (uint64_t)W; }
+
+// duration classes inside a shape bucket (longest-processing-time-first order of the persistent launches)
+constexpr int kNumCls = 24;
+TRPA_HD uint32_t duration_class(uint64_t time) {
+  uint32_t l = 0;
+  while (time > 1u) { time >>= 1; ++l; }
+  return l < 8u ? 0u : (l - 8u < (uint32_t)kNumCls ? l - 8u : (uint32_t)kNumCls - 1u);
+}
 
 struct ShapeCost { uint64_t time, cost; };   // time: alu instructions on the critical lane; cost = time * L
 TRPA_HD ShapeCost band_shape_cost(const BandGeom& g, int widx, int lidx, const PlanParams& pp) {

@@ -24,6 +24,8 @@ constexpr uint32_t kHintIsBound = 0x80000000u;
 // pattern row | rows of full width), 0 = the plain band.
 struct PairDesc {
   uint32_t a, b, out, pad, aux;
+  uint32_t cls;   // after planning: duration class of the pair (log2 of the planner's time estimate); the
+                  // pairs of a shape bucket are launched longest class first
 };
 
 // One segment-staging request: cut [begin, begin+descs[desc].len) (0-based) out of sequence `seq`

@@ -385,7 +385,6 @@ struct Machine {
     float dist = 0.f;
 
     if (S.phase == PH_P0_WAIT) {
-      const uint32_t qrlength = S.qrlength;
       uint32_t ibest = 0;
       uint32_t support = 0;
       uint32_t lca_all = rec[0].node;

@@ -69,6 +69,25 @@ ALU_OPS_PER_WORDSTEP = 10.0
 ALU_OPS_PER_WORDSTEP_R01 = 10.4
 
 
+# stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version banner, ...) is
+# sent to stderr by pointing fd 1 at fd 2 for the whole run; emit() writes to the saved real stdout.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(text):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
 def make_data(workload, seed, n_queries=None):
     w = WORKLOADS[workload]
     cfg = dict(w["cfg"])
@@ -177,7 +196,7 @@ def reference_arm(args, rank, world):
         for it in range(args.warmup + args.steps):
             dt, _ = run_reference_binary(d, cores, keep_dir=tmp)
             if dt is None:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/taxator was not built"}))
+                emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/taxator was not built"}))
                 return
             if it >= args.warmup:
                 times.append(dt)
@@ -197,7 +216,7 @@ def reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def lca_bench(args, rank, local_rank, world):
@@ -219,13 +238,13 @@ def lca_bench(args, rank, local_rank, world):
         for it in range(args.warmup + args.steps):
             dt, _ = run_reference_binary(sub, cores, model_args=["-a", "megan-lca"])
             if dt is None:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/taxator was not built"}))
+                emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/taxator was not built"}))
                 return
             if it >= args.warmup:
                 times.append(dt)
         nseg_sub = len(synth.segments_fast(sub)[0])
         v = nseg_sub / (sum(times) / len(times))
-        print(json.dumps({"impl": "reference", "metric": "query segments/sec (taxator -a megan-lca)", "value": v, "unit": "segments/s",
+        emit(json.dumps({"impl": "reference", "metric": "query segments/sec (taxator -a megan-lca)", "value": v, "unit": "segments/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
                           "config": {"workload": "lca: megan-lca on the record tables of c2", "segments_per_step": nseg_sub},
@@ -310,7 +329,7 @@ def lca_bench(args, rank, local_rank, world):
                                     "sample": "first %d segments; oracle/_ref/taxator -a megan-lca -p %d, wall %.2f s incl. start-up and parsing" % (nsub, cores, dt),
                                     "gff3_identical_to_gpu": ours == ref_lines}
     if rank == 0:
-        print(json.dumps(line))
+        emit(json.dumps(line))
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -330,6 +349,7 @@ def main():
     ap.add_argument("--tune", action="append", default=[], help="key=value tuning hook (trpa_set_tuning)")
     ap.add_argument("--band", type=int, default=1, help="1: exact Ukkonen band (default), 0: full DP matrices (A/B)")
     args = ap.parse_args()
+    capture_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -554,7 +574,7 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "segments/s", "cores": cores, "kind": "reference",
                                     "sample": "oracle/_ref/taxator missing"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(json.dumps(line))
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -50,6 +50,14 @@ LCA_VARIANTS = {
 }
 
 
+def lca_masked(d):
+    """records masked in the input ('*' prefix, AlignmentRecord::isFiltered): every 17th line and ALL lines of
+    the fourth query (a record set without any active record)"""
+    import numpy as np
+    n = len(d.rec["q"])
+    return (np.arange(n) % 17 == 5) | (d.rec["q"] == 3)
+
+
 def lca_case_data(name):
     """(SynthData with quantised scores, evalue per record in FILE order, unclassified-name flag per node)."""
     import numpy as np
@@ -81,10 +89,12 @@ def lca_write_files(d, evalue, named, outdir):
         for i, t in enumerate(d.tax_ids):
             f.write("%d\t|\t%snode%d\t|\t\t|\tscientific name\t|\n" % (t, "unclassified " if named[i] else "", t))
     r = d.rec
+    masked = lca_masked(d)
     with open(os.path.join(outdir, "alignments.tsv"), "w") as f:
         for k in range(len(r["q"])):
             qi = r["q"][k]
-            f.write("%s\t%d\t%d\t%d\t%s\t%d\t%d\t%s\t%s\t%d\t%d\n" % (
+            f.write("%s%s\t%d\t%d\t%d\t%s\t%d\t%d\t%s\t%s\t%d\t%d\n" % (
+                "*" if masked[k] else "",
                 d.q_names[qi], r["qstart"][k], r["qstop"][k], len(d.q_seqs[qi]), d.ref_names[r["r"][k]], r["rstart"][k],
                 r["rstop"][k], repr(float(r["score"][k])), repr(float(evalue[k])), r["ident"][k], r["alnlen"][k]))
 
@@ -95,8 +105,16 @@ def lca_flat(d, evalue):
     r = d.rec
     nrec = len(r["q"])
     order = np.lexsort((np.arange(nrec), r["qstop"], r["qstart"], r["q"]))
-    segs, cands = d.segments()
-    return segs, cands, np.ascontiguousarray(evalue[order])
+    segs, cands = d.segments()           # record sets are formed from ALL records, masked or not
+    keep = ~lca_masked(d)[order]         # ... and only the unmasked ones go into the candidate table
+    ev = evalue[order]
+    csum = np.concatenate([[0], np.cumsum(keep)])
+    out = segs.copy()
+    for i, sg in enumerate(segs):
+        b, c = int(sg["cand_begin"]), int(sg["cand_count"])
+        out[i]["cand_begin"] = csum[b]
+        out[i]["cand_count"] = csum[b + c] - csum[b]
+    return out, np.ascontiguousarray(cands[keep]), np.ascontiguousarray(ev[keep])
 
 
 def lca_golden_lines(case, variant):

@@ -87,11 +87,13 @@ struct Rec {
   uint32_t qstart, qstop, qlen, ord, node, rstart, rstop, ident, alnlen;
   float score;
   uint32_t masked;
+  double evalue;
 };
 
 struct Piece {
   std::vector<trpa_segment> segs;
   std::vector<trpa_candidate> cands;
+  std::vector<double> evalue;
   std::vector<SegMeta> meta;
   std::exception_ptr err;
   size_t err_off = 0;
@@ -191,7 +193,7 @@ void FastIngest::parse_block(FlatBlock& out, size_t len) {
     cutp[t] = std::max(p, cutp[t - 1]);
   }
   std::vector<Piece> pieces(T);
-  const bool split = opt_.split;
+  const bool split = opt_.split, need_stores = opt_.need_stores, want_evalue = opt_.want_evalue;
 
   parallel_for(T, [&](unsigned t) {
     Piece& P = pieces[t];
@@ -224,17 +226,18 @@ void FastIngest::parse_block(FlatBlock& out, size_t len) {
         for (uint32_t k = i; k < j; ++k) {
           const Rec& r = grp[order[k]];
           if (r.masked) continue;   // active_records, hh:350-356
-          if (r.ord == RefResolver::kNone) throw SequenceNotFound("bad sequence identifier: " + std::string(r.rid, r.rid_len));
+          if (need_stores && r.ord == RefResolver::kNone) throw SequenceNotFound("bad sequence identifier: " + std::string(r.rid, r.rid_len));
           trpa_candidate c;
-          c.ref_seq = r.ord; c.rstart = r.rstart; c.rstop = r.rstop; c.qstart = r.qstart; c.qstop = r.qstop;
+          c.ref_seq = need_stores ? r.ord : 0u; c.rstart = r.rstart; c.rstop = r.rstop; c.qstart = r.qstart; c.qstop = r.qstop;
           c.score = r.score; c.identities = r.ident; c.alnlen = r.alnlen; c.node = r.node;
           P.cands.push_back(c);
+          if (want_evalue) P.evalue.push_back(r.evalue);
           ++cnt;
         }
         sg.cand_count = cnt;
         const Rec& first = grp[order[i]];
         // the reference looks the query up only when it realigns (n >= 2, hh:415)
-        sg.query_seq = cnt >= 2 ? q_store_.ordinal(std::string(first.qid, first.qid_len)) : 0u;
+        sg.query_seq = need_stores && cnt >= 2 ? q_store_.ordinal(std::string(first.qid, first.qid_len)) : 0u;
         P.segs.push_back(sg);
         P.meta.push_back(SegMeta{first.qid, first.qid_len, first.qlen, cnt ? 1u : 0u});
         i = j;
@@ -278,12 +281,13 @@ void FastIngest::parse_block(FlatBlock& out, size_t len) {
           r.qid = f[0]; r.qid_len = (uint32_t)(fe[0] - f[0]);
           r.rid = f[4]; r.rid_len = (uint32_t)(fe[4] - f[4]);
           r.ord = ent->ordinal; r.node = ent->node;
+          r.evalue = evalue;
         } else {
           // anything unusual: the record-at-a-time parser decides (same acceptance, same errors)
           AlignmentRecord* a = parse_alignment_line(std::string(p, (size_t)(e - p)), mapping_, tax_);
           r.masked = a->masked ? 1u : 0u;
           r.qstart = a->qstart; r.qstop = a->qstop; r.qlen = a->qlen; r.rstart = a->rstart; r.rstop = a->rstop;
-          r.score = a->score; r.ident = a->identities; r.alnlen = a->alnlen; r.node = a->node;
+          r.score = a->score; r.ident = a->identities; r.alnlen = a->alnlen; r.node = a->node; r.evalue = a->evalue;
           const std::string_view qv = line_qid(p, e);
           r.qid = qv.data(); r.qid_len = (uint32_t)qv.size();
           // the reference id is the 5th field of the line however odd the rest was
@@ -332,6 +336,7 @@ void FastIngest::parse_block(FlatBlock& out, size_t len) {
   for (unsigned t = 0; t < T; ++t) { soff[t] = ns; coff[t] = nc; ns += pieces[t].segs.size(); nc += pieces[t].cands.size(); }
   if (nc >= 0xfffffff0ull || ns >= 0xfffffff0ull) throw TaxatorError("alignment block too large; lower --batch-bytes");
   out.segs.resize(ns); out.cands.resize(nc); out.meta.resize(ns);
+  out.evalue.resize(opt_.want_evalue ? nc : 0);
   parallel_for(T, [&](unsigned t) {
     Piece& P = pieces[t];
     for (size_t i = 0; i < P.segs.size(); ++i) {
@@ -341,6 +346,7 @@ void FastIngest::parse_block(FlatBlock& out, size_t len) {
     }
     if (!P.meta.empty()) memcpy(&out.meta[soff[t]], P.meta.data(), P.meta.size() * sizeof(SegMeta));
     if (!P.cands.empty()) memcpy(&out.cands[coff[t]], P.cands.data(), P.cands.size() * sizeof(trpa_candidate));
+    if (!P.evalue.empty()) memcpy(&out.evalue[coff[t]], P.evalue.data(), P.evalue.size() * sizeof(double));
   });
 }
 
@@ -460,6 +466,15 @@ class BoundedQueue {
 uint64_t run_prediction_fast(FILE* in, const SeqIdMapping& mapping, const FlatTaxonomy& tax, const SeqStore& q_store,
                              const SeqStore& db_store, const IngestOptions& opt, const FlatPredictor& predict,
                              std::ostream& out, std::ostream* statslog, PredictStats* stats, StageTimes* times) {
+  return run_prediction_fast_blocks(
+      in, mapping, tax, q_store, db_store, opt,
+      [&](FlatBlock& b) { predict(b.segs.data(), (uint32_t)b.segs.size(), b.cands.data(), (uint32_t)b.cands.size(), b.res.data()); },
+      out, statslog, stats, times);
+}
+
+uint64_t run_prediction_fast_blocks(FILE* in, const SeqIdMapping& mapping, const FlatTaxonomy& tax, const SeqStore& q_store,
+                                    const SeqStore& db_store, const IngestOptions& opt, const BlockPredictor& predict,
+                                    std::ostream& out, std::ostream* statslog, PredictStats* stats, StageTimes* times) {
   out << kGFF3Header;
   typedef std::chrono::steady_clock Clock;
   auto secs = [](Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
@@ -517,7 +532,7 @@ uint64_t run_prediction_fast(FILE* in, const SeqIdMapping& mapping, const FlatTa
     while (parsed.pop(b)) {
       b->res.resize(b->segs.size());
       const auto t0 = Clock::now();
-      predict(b->segs.data(), (uint32_t)b->segs.size(), b->cands.data(), (uint32_t)b->cands.size(), b->res.data());
+      predict(*b);
       st.predict_s += secs(t0, Clock::now());
       st.blocks++;
       if (!placed.push(std::move(b))) break;

@@ -58,6 +58,7 @@ struct FlatBlock {
   std::vector<char> text;            // owns what SegMeta::qid points into
   std::vector<trpa_segment> segs;
   std::vector<trpa_candidate> cands;
+  std::vector<double> evalue;        // one per candidate (IngestOptions::want_evalue)
   std::vector<SegMeta> meta;
   std::vector<trpa_result> res;
   uint64_t first_line = 0;           // line number (1-based) of the block's first line
@@ -68,6 +69,9 @@ struct IngestOptions {
   size_t block_bytes = 128u << 20;   // text per block (a block always ends at a query boundary)
   unsigned threads = 0;              // 0: hardware concurrency (max 32)
   size_t min_parallel_bytes = 1u << 20;  // smaller blocks are parsed by one thread
+  // the alignment-free models read no sequence stores (ordinals stay 0) but need the e-value column
+  bool need_stores = true;
+  bool want_evalue = false;
 };
 
 class FastIngest {
@@ -92,6 +96,8 @@ class FastIngest {
 
 // results of a flat batch (any device, any shard order) -> results array
 typedef std::function<void(const trpa_segment*, uint32_t, const trpa_candidate*, uint32_t, trpa_result*)> FlatPredictor;
+// same, with the whole block (e-values): fills b.res
+typedef std::function<void(FlatBlock&)> BlockPredictor;
 
 // GFF3 lines of a block, formatted in parallel; carry = (ival, signal) of the previous record
 // (n == 0 sets inherit them: hh:359-368, taxator.cpp:66); updated to the block's last record
@@ -103,5 +109,8 @@ struct StageTimes { double ingest_s = 0, predict_s = 0, output_s = 0; uint64_t b
 uint64_t run_prediction_fast(FILE* in, const SeqIdMapping& mapping, const FlatTaxonomy& tax, const SeqStore& q_store,
                              const SeqStore& db_store, const IngestOptions& opt, const FlatPredictor& predict,
                              std::ostream& out, std::ostream* statslog, PredictStats* stats, StageTimes* times = nullptr);
+uint64_t run_prediction_fast_blocks(FILE* in, const SeqIdMapping& mapping, const FlatTaxonomy& tax, const SeqStore& q_store,
+                                    const SeqStore& db_store, const IngestOptions& opt, const BlockPredictor& predict,
+                                    std::ostream& out, std::ostream* statslog, PredictStats* stats, StageTimes* times = nullptr);
 
 }  // namespace taxator_b200

@@ -62,6 +62,15 @@ void LCAPredictionModelGPU::predictBatch(std::vector<RecordSet>& recordsets, std
   }
 }
 
+void LCAPredictionModelGPU::predictFlat(const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands,
+                                        uint32_t n_cands, const double* evalue, trpa_result* res) {
+  if (!n_segs) return;
+  std::lock_guard<std::mutex> lock(mutex_);
+  if (trpa_predict_lca_batch(ctx_, &params_, segs, n_segs, cands, n_cands, evalue,
+                             tax_->unclassified.empty() ? nullptr : tax_->unclassified.data(), res, 1, nullptr))
+    throw TaxatorError(std::string("GPU prediction: ") + trpa_last_error());
+}
+
 void LCAPredictionModelGPU::predict(RecordSet& recordset, PredictionRecord& prec, std::ostream& logsink) {
   std::vector<RecordSet> one(1);
   one[0].swap(recordset);

@@ -34,6 +34,9 @@ class LCAPredictionModelGPU : public TaxonPredictionModel<RecordSet> {
   ~LCAPredictionModelGPU() override;
   void predict(RecordSet& recordset, PredictionRecord& prec, std::ostream& logsink) override;
   void predictBatch(std::vector<RecordSet>& recordsets, std::vector<PredictionRecord>& precs, std::ostream& logsink);
+  // the flat tables of the C ABI in, result records out (what the fast ingest path of the CLI calls; ingest.h)
+  void predictFlat(const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands, uint32_t n_cands,
+                   const double* evalue, trpa_result* res);
 
  private:
   trpa_lca_params params_;

@@ -183,11 +183,28 @@ int main(int argc, char** argv) {
       std::ofstream logsink(opt.logfile.c_str(), std::ios_base::app);
       LCAPredictionModelGPU model(&tax, params, opt.gpus.empty() ? 0 : opt.gpus[0]);
       std::ios::sync_with_stdio(false);
-      RecordSetReader reader(std::cin, mapping, tax, opt.split_alignments, opt.alignments_sorted);
-      run_prediction_stream(
-          reader, tax, opt.batch_segments,
-          [&](std::vector<RecordSet>& sets, std::vector<PredictionRecord>& precs, std::ostream& log) { model.predictBatch(sets, precs, log); },
-          std::cout, logsink);
+      if (opt.legacy_ingest || opt.alignments_sorted) {
+        RecordSetReader reader(std::cin, mapping, tax, opt.split_alignments, opt.alignments_sorted);
+        run_prediction_stream(
+            reader, tax, opt.batch_segments,
+            [&](std::vector<RecordSet>& sets, std::vector<PredictionRecord>& precs, std::ostream& log) { model.predictBatch(sets, precs, log); },
+            std::cout, logsink);
+      } else {
+        // block-parallel parser -> flat tables (+ e-values) -> GPU -> parallel GFF3 formatter; no sequence stores
+        IngestOptions io;
+        io.split = opt.split_alignments;
+        io.block_bytes = opt.batch_bytes;
+        io.need_stores = false;
+        io.want_evalue = true;
+        const SeqStore no_store;
+        run_prediction_fast_blocks(
+            stdin, mapping, tax, no_store, no_store, io,
+            [&](FlatBlock& b) {
+              model.predictFlat(b.segs.data(), (uint32_t)b.segs.size(), b.cands.data(), (uint32_t)b.cands.size(),
+                                b.evalue.data(), b.res.data());
+            },
+            std::cout, nullptr, nullptr);
+      }
       return EXIT_SUCCESS;
     }
     if (opt.dataformat != "nucleotide" && opt.dataformat != "protein") {

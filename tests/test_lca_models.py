@@ -101,10 +101,12 @@ def test_cli_matches_reference_gff3(tmp_path):
     tmp = str(tmp_path / case)
     gu.lca_write_files(d, evalue, named, tmp)
     env = dict(os.environ, TAXATORTK_TAXONOMY_NCBI=tmp)
-    for variant, (args, _) in gu.LCA_VARIANTS.items():
-        with open(os.path.join(tmp, "alignments.tsv"), "rb") as fin:
-            out = subprocess.run([exe] + args + ["-g", "mapping.tax", "-p", "1", "-o", "0", "--batch-segments", "50"], cwd=tmp,
-                                 env=env, stdin=fin, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout.decode()
-        assert out.startswith("##gff-version 3\n")
-        lines = sorted(l + "\n" for l in out.splitlines() if not l.startswith("##"))
-        assert lines == gu.lca_golden_lines(case, variant), variant
+    # the block-parallel ingest (default, small blocks so that several are in flight) and the record-at-a-time path
+    for extra in (["--batch-bytes", "20000"], ["--legacy-ingest", "--batch-segments", "50"]):
+        for variant, (args, _) in gu.LCA_VARIANTS.items():
+            with open(os.path.join(tmp, "alignments.tsv"), "rb") as fin:
+                out = subprocess.run([exe] + args + ["-g", "mapping.tax", "-p", "1", "-o", "0"] + extra, cwd=tmp,
+                                     env=env, stdin=fin, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout.decode()
+            assert out.startswith("##gff-version 3\n")
+            lines = sorted(l + "\n" for l in out.splitlines() if not l.startswith("##"))
+            assert lines == gu.lca_golden_lines(case, variant), (variant, extra)

@@ -178,10 +178,15 @@ int main(int argc, char** argv) {
         std::cout << "classification algorithm can either be: rpa (default), simple-lca, megan-lca, ic-megan-lca, n-best-lca" << std::endl;
         return EXIT_FAILURE;
       }
+      // CUDA context creation (about a second) overlaps the loading of the taxonomy and the mapping
+      const int device = opt.gpus.empty() ? 0 : opt.gpus[0];
+      std::thread warm([device]() { trpa_ctx* c = trpa_create(device, nullptr); if (c) trpa_destroy(c); });
+      struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } warm_joiner{warm};
       FlatTaxonomy tax = load_taxonomy_from_environment(opt.ranks, opt.delete_unmarked);
       SeqIdMapping mapping = load_mapping(opt.mapping);
       std::ofstream logsink(opt.logfile.c_str(), std::ios_base::app);
-      LCAPredictionModelGPU model(&tax, params, opt.gpus.empty() ? 0 : opt.gpus[0]);
+      warm.join();
+      LCAPredictionModelGPU model(&tax, params, device);
       std::ios::sync_with_stdio(false);
       if (opt.legacy_ingest || opt.alignments_sorted) {
         RecordSetReader reader(std::cin, mapping, tax, opt.split_alignments, opt.alignments_sorted);

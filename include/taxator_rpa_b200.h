@@ -122,8 +122,12 @@ int trpa_set_lookahead(trpa_ctx* ctx, int k);
 int trpa_set_band(trpa_ctx* ctx, int on);
 /* Test / tuning hooks (results never depend on them): "band_k0" = forced initial band threshold
  * (exercises the verify-and-widen loop), "wedge" = 0 keeps the band at constant width (1: let it narrow
- * where the kernel's certificate proves that exact), "plan_lanes" = lanes the shape planner assumes,
- * "myers_version" = 2 selects the previous full-matrix kernel for A/B runs. */
+ * where the kernel's certificate proves that exact), "plan_lanes" = weight of a pair's latency in the shape
+ * planner (0: the resident lanes), "tail_log2" = its convex term time^2 / 2^tail_log2, "hint_mul64" /
+ * "hint_add" = safety margin on distance estimates, "cost_word10" / "cost_col10" / "cost_step" / "cost_setup" /
+ * "cost_setup_w" = the planner's instruction-cost model, "la_cap" / "la_max" = look-ahead budget per round /
+ * per segment, "force_shape" = one kernel shape for every pair, "myers_version" = 2 selects the previous
+ * full-matrix kernel for A/B runs. */
 int trpa_set_tuning(trpa_ctx* ctx, const char* key, int64_t value);
 int trpa_profile_reset(trpa_ctx* ctx);
 int trpa_profile_get(trpa_ctx* ctx, trpa_profile* out);

@@ -181,17 +181,35 @@ __global__ void stage_nt_kernel(const StageReq* __restrict__ reqs, u32 n_req,
     const u32* sn = rq.store ? r_n + r_woff[rq.seq] : q_n + q_woff[rq.seq];
     const u32 nwords = (d.len + 31) >> 5;
     u32 anyn = 0;
+    // 32 consecutive bits of the three planes starting at bit position s of the source (one 8-byte and one
+    // 4-byte load per source word instead of one load per plane; bits below 0 read as 0)
+    auto window3 = [&](long long s, u32& w0, u32& w1, u32& wn) {
+      if (s < 0) {
+        const u32 sh = (u32)(-s);
+        if (sh >= 32) { w0 = w1 = wn = 0u; return; }
+        const uint2 a = sp[0];
+        w0 = a.x << sh; w1 = a.y << sh; wn = sn[0] << sh;
+        return;
+      }
+      const u64 w = (u64)s >> 5; const u32 sh = (u32)s & 31;
+      const uint2 a = sp[w];
+      const u32 na = sn[w];
+      if (!sh) { w0 = a.x; w1 = a.y; wn = na; return; }
+      const uint2 b = sp[w + 1];
+      const u32 nb = sn[w + 1];
+      w0 = __funnelshift_r(a.x, b.x, sh); w1 = __funnelshift_r(a.y, b.y, sh); wn = __funnelshift_r(na, nb, sh);
+    };
+#pragma unroll 2
     for (u32 k = lane; k < nwords; k += 32) {
       const u32 rem = d.len - 32 * k;
       const u32 valid = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
       u32 p0, p1, pn;
       if (!rq.rev) {
-        const long long s = (long long)rq.begin + 32ll * k;
-        p0 = window_x(sp, s); p1 = window_y(sp, s); pn = window_n(sn, s);
+        window3((long long)rq.begin + 32ll * k, p0, p1, pn);
       } else {
         // out base j = complement(src[begin + len - 1 - j])
-        const long long s = (long long)rq.begin + (long long)d.len - 32ll * k - 32ll;
-        p0 = ~__brev(window_x(sp, s)); p1 = ~__brev(window_y(sp, s)); pn = __brev(window_n(sn, s));
+        window3((long long)rq.begin + (long long)d.len - 32ll * k - 32ll, p0, p1, pn);
+        p0 = ~__brev(p0); p1 = ~__brev(p1); pn = __brev(pn);
       }
       pn &= valid;
       p0 &= valid & ~pn; p1 &= valid & ~pn;

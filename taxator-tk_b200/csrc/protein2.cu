@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "launch.h"
 #include "blosum62_table.h"
+#include <cstdlib>
 
 namespace trpa {
 
@@ -39,6 +40,13 @@ static cudaError_t ensure_table2() {
 }
 
 __device__ __forceinline__ int max3i(int a, int b, int c) { return max(max(a, b), c); }
+
+// half-warp variant (protein2h_kernel below): pairs with |A| <= 320 columns
+constexpr int kHMaxCols = 320;
+constexpr int kHCQ = 5;   // profile capacity of the half-warp kernel: 20 columns per lane
+
+// true: the pair is computed by protein2h_kernel (and skipped by protein2_kernel)
+__device__ __forceinline__ bool p2h_takes(int n, int m) { return n > 0 && m > 0 && n <= kHMaxCols && m <= kP2MaxLen; }
 
 constexpr int SH = 13;
 constexpr int PRIO_MASK = 3 << 11;
@@ -151,7 +159,7 @@ __device__ __forceinline__ int protein2_strip(const uint8_t* __restrict__ a, con
 __global__ void __launch_bounds__(128)
 protein2_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __restrict__ seqs,
                 const uint8_t* __restrict__ residues, int2* __restrict__ out2, int2* __restrict__ scratch,
-                u32 scratch_stride, u32 cq_rt) {
+                u32 scratch_stride, u32 cq_rt, int skip_cols) {
   // cq_rt: column quads per lane the shared-memory profile is sized for (the launch's longest sequence decides:
   // 300-aa batches need 3 instead of 4 quads and fit a fifth CTA per SM)
   extern __shared__ __align__(16) signed char prof_all[];
@@ -167,6 +175,7 @@ protein2_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __
   const int n = (int)A.len;  // columns (H)
   const int m = (int)B.len;  // rows (V)
   if (n > kP2MaxLen || m > kP2MaxLen) return;  // left to protein_kernel
+  if (skip_cols && p2h_takes(n, m)) return;    // done by protein2h_kernel
   const uint8_t* a = residues + A.woff;
   const uint8_t* b = residues + B.woff;
   if (n == 0 || m == 0) {
@@ -196,6 +205,142 @@ protein2_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __
   }
 }
 
+// ---- half-warp variant: TWO pairs per warp, 16 lanes and up to 20 columns per lane each (|A| <= 320, one strip).
+// For the 300-aa pairs of C3 the wavefront ramp shrinks from 31 to 15 steps and the per-step bookkeeping is
+// shared by 40 instead of 20 cells.  Same packed cells, same per-lane profile layout (bank == warp lane), same
+// two rows per step as protein2_strip; pairs that do not fit are left to protein2_kernel / protein_kernel.
+
+template <int C>
+__device__ __forceinline__ void protein2h_run(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n, int m,
+                                              bool mine, unsigned char* prof, const signed char* tbl, u32 lp,
+                                              int2* __restrict__ out2, u32 oidx) {
+  constexpr int CQ = (C + 3) / 4;
+  const int pad = 16 * C - n;                     // leading padding columns (right-aligned)
+  const int v1 = (int)lp * C - pad;               // index of this lane's first column (may be < 0)
+  int up[C];
+  int ac[CQ * 4];
+#pragma unroll
+  for (int c = 0; c < CQ * 4; ++c) {
+    const int v = v1 + c;
+    ac[c] = (c < C && v >= 0 && mine) ? (int)a[v] : -1;
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) up[c] = (v1 + c >= 0) ? p2_boundary(v1 + c + 1) : 0;
+  for (int bb = 0; bb < 27; ++bb) {
+#pragma unroll
+    for (int q = 0; q < CQ; ++q) {
+      u32 w = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = ac[4 * q + k];
+        const int e = r >= 0 ? 2 * tbl[r * 32 + bb] + 9 : 0;
+        w |= (u32)(uint8_t)e << (8 * k);
+      }
+      *reinterpret_cast<u32*>(prof + (bb * CQ + q) * 128) = w;
+    }
+  }
+  __syncwarp();
+  int diag0 = (v1 - 1 >= 0) ? p2_boundary(v1) : p2_boundary(0);   // cell(0, first column - 1)
+  const u32 prof_sa = (u32)__cvta_generic_to_shared(prof);
+  auto row = [&](u32 prow, int left, int diag) -> int {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      int e;
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(e) : "r"(prow + (u32)((c >> 2) * 128 + (c & 3))));
+      const int D = e * (1 << (SH - 1)) + diag;
+      const int V = up[c] + CV;
+      const int H = left + CH;
+      const int cell = max3i(D, V, H) & ~PRIO_MASK;
+      diag = up[c];
+      up[c] = cell;
+      left = cell;
+    }
+    return left;
+  };
+  const int mo = __shfl_xor_sync(0xffffffffu, m, 16);
+  const int steps = (((m > mo ? m : mo) + 1) >> 1) + 15;
+  int last0 = 0, last1 = 0, res = 0;
+  for (int t = 1; t <= steps; ++t) {
+    const int recv0 = __shfl_up_sync(0xffffffffu, last0, 1, 16);
+    const int recv1 = __shfl_up_sync(0xffffffffu, last1, 1, 16);
+    const int i0 = 2 * (t - (int)lp) - 1, i1 = i0 + 1;
+    if (i0 >= 1 && i0 <= m) {
+      int left0, left1;
+      if (lp == 0) { left0 = p2_boundary(i0) + i0 * ROWBIAS; left1 = p2_boundary(i1) + i1 * ROWBIAS; }
+      else { left0 = recv0; left1 = recv1; }
+      const u32 prow0 = prof_sa + (u32)b[i0 - 1] * (u32)(CQ * 128);
+      const u32 prow1 = prof_sa + (u32)b[(i1 <= m ? i1 : m) - 1] * (u32)(CQ * 128);
+      const int l0 = row(prow0, left0, diag0);
+      const int l1 = row(prow1, left1, left0);
+      diag0 = left1;
+      last0 = l0; last1 = l1;
+      if (lp == 15) { if (i0 == m) res = l0; else if (i1 == m) res = l1; }
+    }
+  }
+  if (lp == 15 && mine) {
+    const int P = res - m * ROWBIAS;
+    const int score = P >> SH;
+    const int gaps = P & 0x7ff;
+    out2[oidx] = make_int2(score, (n + m - gaps) / 2);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+protein2h_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __restrict__ seqs,
+                 const uint8_t* __restrict__ residues, int2* __restrict__ out2) {
+  extern __shared__ __align__(16) signed char prof_all[];
+  signed char* tbl = prof_all + (size_t)kP2Warps * 27 * kHCQ * 128;   // BLOSUM62 [a][b]
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) tbl[i] = c_blosum_p2[i >> 5][i & 31];
+  __syncthreads();
+  const u32 lane = threadIdx.x & 31, lp = lane & 15u;
+  const u32 warp_in_cta = threadIdx.x >> 5;
+  const u32 warp_gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 pidx = warp_gid * 2u + (lane >> 4);
+  int n = 0, m = 0;
+  const uint8_t* a = residues;
+  const uint8_t* b = residues;
+  u32 oidx = 0;
+  bool mine = false;   // this half's pair is handled here
+  if (pidx < count) {
+    const PairDesc pd = pairs[pidx];
+    const SeqDesc A = seqs[pd.a], B = seqs[pd.b];
+    if (p2h_takes((int)A.len, (int)B.len)) {
+      mine = true; n = (int)A.len; m = (int)B.len; oidx = pd.out;
+      a = residues + A.woff; b = residues + B.woff;
+    }
+  }
+  if (!__any_sync(0xffffffffu, mine)) return;
+  // both halves use the lane width (columns per lane) the longer of the two pairs needs
+  const int no = __shfl_xor_sync(0xffffffffu, n, 16);
+  const int cols = ((n > no ? n : no) + 15) >> 4;
+  unsigned char* prof = reinterpret_cast<unsigned char*>(prof_all) + ((size_t)warp_in_cta * 27 * kHCQ * 32 + lane) * 4;  // [b][c/4][lane][c%4]
+  if (cols <= 8) protein2h_run<8>(a, b, n, m, mine, prof, tbl, lp, out2, oidx);
+  else if (cols <= 12) protein2h_run<12>(a, b, n, m, mine, prof, tbl, lp, out2, oidx);
+  else if (cols <= 16) protein2h_run<16>(a, b, n, m, mine, prof, tbl, lp, out2, oidx);
+  else protein2h_run<20>(a, b, n, m, mine, prof, tbl, lp, out2, oidx);
+}
+
+static bool protein_half_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TRPA_PROTEIN_HALF"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+static cudaError_t launch_h(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues, int2* out2,
+                            cudaStream_t stream) {
+  const size_t smem = (size_t)kP2Warps * 27 * kHCQ * 128 + 27 * 32;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(protein2h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const u32 warps = (count + 1u) / 2u;
+  const u32 blocks = (warps + kP2Warps - 1) / kP2Warps;
+  protein2h_kernel<<<blocks, 32 * kP2Warps, smem, stream>>>(pairs, count, seqs, residues, out2);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_protein2(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,
                             int2* out2, int2* scratch, u32 scratch_stride, u32 max_len, cudaStream_t stream) {
   if (count == 0) return cudaSuccess;
@@ -207,6 +352,8 @@ cudaError_t launch_protein2(const PairDesc* pairs, u32 count, const SeqDesc* seq
     if (e != cudaSuccess) return e;
     attr = true;
   }
+  const bool half = protein_half_enabled();
+  if (half) { e = launch_h(pairs, count, seqs, residues, out2, stream); if (e != cudaSuccess) return e; }
   const u32 blocks = (count + kP2Warps - 1) / kP2Warps;
   // profile capacity: columns per lane of the longest strip any pair of this launch can have
   const u32 longest = max_len ? (max_len > (u32)kP2MaxLen ? (u32)kP2MaxLen : max_len) : (u32)kP2MaxLen;
@@ -215,7 +362,7 @@ cudaError_t launch_protein2(const PairDesc* pairs, u32 count, const SeqDesc* seq
   // the strip templates round the columns per lane up to 4, 8, 10, 12 or 16
   const u32 cq = cols <= 4 ? 1u : (cols <= 8 ? 2u : (cols <= 12 ? 3u : 4u));
   const size_t smem = (size_t)kP2Warps * 27 * cq * 128 + 27 * 32;
-  protein2_kernel<<<blocks, 32 * kP2Warps, smem, stream>>>(pairs, count, seqs, residues, out2, scratch, scratch_stride, cq);
+  protein2_kernel<<<blocks, 32 * kP2Warps, smem, stream>>>(pairs, count, seqs, residues, out2, scratch, scratch_stride, cq, half ? 1 : 0);
   return cudaGetLastError();
 }
 

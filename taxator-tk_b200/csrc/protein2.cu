@@ -89,7 +89,7 @@ __device__ __forceinline__ int protein2_strip(const uint8_t* __restrict__ a, con
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int r = ac[4 * q + k];
-        const int e = r >= 0 ? 2 * tbl[r * 32 + bb] + 9 : 0;
+        const int e = r >= 0 ? 2 * tbl[bb * 32 + r] + 9 : 0;   // BLOSUM62 is symmetric: [bb][r] keeps the lanes of a warp on distinct banks (or the same word)
         w |= (u32)(uint8_t)e << (8 * k);
       }
       *reinterpret_cast<u32*>(prof + (bb * CQ + q) * 128) = w;
@@ -233,7 +233,7 @@ __device__ __forceinline__ void protein2h_run(const uint8_t* __restrict__ a, con
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int r = ac[4 * q + k];
-        const int e = r >= 0 ? 2 * tbl[r * 32 + bb] + 9 : 0;
+        const int e = r >= 0 ? 2 * tbl[bb * 32 + r] + 9 : 0;   // BLOSUM62 is symmetric: [bb][r] keeps the lanes of a warp on distinct banks (or the same word)
         w |= (u32)(uint8_t)e << (8 * k);
       }
       *reinterpret_cast<u32*>(prof + (bb * CQ + q) * 128) = w;

@@ -151,7 +151,7 @@ TRPA_HD uint64_t band_steps(const BandGeom& g, int W, int L) {
   uint64_t off = 0;
   if (S > (uint32_t)L) {
     const uint32_t rounds = (S - 1u) / (uint32_t)L;          // rounds that have a successor round
-    const uint32_t stride = rounds > 12u ? (rounds + 11u) / 12u : 1u;
+    const uint32_t stride = rounds > 5u ? (rounds + 4u) / 5u : 1u;   // 5 samples: the planner is instruction bound on this loop
     uint64_t acc = 0;
     uint32_t n = 0;
     for (uint32_t r = 0; r < rounds; r += stride, ++n) acc += (uint64_t)L + (uint64_t)g.round_gap(r, (uint32_t)W, (uint32_t)L, S);

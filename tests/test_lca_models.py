@@ -110,3 +110,44 @@ def test_cli_matches_reference_gff3(tmp_path):
             assert out.startswith("##gff-version 3\n")
             lines = sorted(l + "\n" for l in out.splitlines() if not l.startswith("##"))
             assert lines == gu.lca_golden_lines(case, variant), (variant, extra)
+
+
+def _build_host_lca_harness():
+    host = os.path.join(ol.ROOT, "taxator-tk_b200", "host")
+    os.makedirs(ol.BUILD_DIR, exist_ok=True)
+    exe = os.path.join(ol.BUILD_DIR, "host_lca_harness")
+    src = os.path.join(ol.ROOT, "tests", "host_lca_harness.cpp")
+    deps = [src] + [os.path.join(host, f) for f in os.listdir(host)]
+    oracle_so = ol.build_oracle()
+    if not ol._newer(exe, *deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ol.ROOT, "include"), "-o", exe, src,
+                               os.path.join(host, "taxonomy.cpp"), os.path.join(host, "seqstore.cpp"),
+                               os.path.join(host, "records.cpp"), os.path.join(host, "rpa_model.cpp"),
+                               os.path.join(host, "ingest.cpp"), oracle_so,
+                               os.path.join(ol.ROOT, "taxator-tk_b200", "lib", "libtaxator_rpa_b200.so"),
+                               "-Wl,-rpath," + ol.ORACLE_DIR,
+                               "-Wl,-rpath," + os.path.join(ol.ROOT, "taxator-tk_b200", "lib"), "-lz", "-lpthread"])
+    return exe
+
+
+@pytest.mark.parametrize("case", gu.LCA_CASES)
+def test_host_path_matches_reference_gff3(tmp_path, case):
+    """CPU: taxonomy loader ('unclassified' flags), parser, store-less block ingest with e-values and the GFF3
+    formatter of the CLI, with the oracle in place of the GPU, on the reference's own input files."""
+    exe = _build_host_lca_harness()
+    d, evalue, named = gu.lca_case_data(case)
+    tmp = str(tmp_path / case)
+    gu.lca_write_files(d, evalue, named, tmp)
+    env = dict(os.environ, TAXATORTK_TAXONOMY_NCBI=tmp)
+    for variant, (_, kw) in gu.LCA_VARIANTS.items():
+        args = [str(kw["model"]), repr(kw.get("toppercent", 0.05)), repr(kw.get("minscore", 0.0)), repr(kw.get("maxevalue", 1000.0)),
+                str(kw.get("minsupport", 1)), str(kw.get("nbest", 1)), "1" if kw.get("ignore_unclassified") else "0"]
+        for block in ("134217728", "30000"):
+            with open(os.path.join(tmp, "alignments.tsv"), "rb") as fin:
+                p = subprocess.run([exe] + args + ["mapping.tax", block], cwd=tmp, env=env, stdin=fin, stdout=subprocess.PIPE,
+                                   stderr=subprocess.PIPE)
+            assert p.returncode == 0, p.stderr.decode()
+            out = p.stdout.decode()
+            assert out.startswith("##gff-version 3\n")
+            lines = sorted(l + "\n" for l in out.splitlines() if not l.startswith("##"))
+            assert lines == gu.lca_golden_lines(case, variant), (variant, block)

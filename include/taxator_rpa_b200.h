@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TRPA_ABI_VERSION 5
+#define TRPA_ABI_VERSION 6
 
 #define TRPA_OK 0
 #define TRPA_ERR_CUDA (-1)
@@ -60,7 +60,10 @@ typedef struct trpa_candidate {
 } trpa_candidate;
 
 /* One query segment == one record set handed to predict() (taxator.cpp:66-72,163-175), unmasked
- * records only, in record-set order (the library applies SortFilter's stable sort itself). */
+ * records only, in record-set order (the library applies SortFilter's stable sort itself).
+ * CONTRACT: the record sets of a table are contiguous and in order -- segs[0].cand_begin == 0 and
+ * segs[s+1].cand_begin == segs[s].cand_begin + segs[s].cand_count -- every entry point that takes a segment
+ * table rejects anything else with TRPA_ERR_ARG (the per-candidate work arrays are laid out by it). */
 typedef struct trpa_segment {
   uint32_t query_seq;   /* ordinal in the query store */
   uint32_t cand_begin;  /* first candidate of this segment in the candidate table */
@@ -126,8 +129,7 @@ int trpa_set_band(trpa_ctx* ctx, int on);
  * planner (0: the resident lanes), "tail_log2" = its convex term time^2 / 2^tail_log2, "hint_mul64" /
  * "hint_add" = safety margin on distance estimates, "cost_word10" / "cost_col10" / "cost_step" / "cost_setup" /
  * "cost_setup_w" = the planner's instruction-cost model, "la_cap" / "la_max" = look-ahead budget per round /
- * per segment, "force_shape" = one kernel shape for every pair, "myers_version" = 2 selects the previous
- * full-matrix kernel for A/B runs. */
+ * per segment, "force_shape" = one kernel shape for every pair. */
 int trpa_set_tuning(trpa_ctx* ctx, const char* key, int64_t value);
 int trpa_profile_reset(trpa_ctx* ctx);
 int trpa_profile_get(trpa_ctx* ctx, trpa_profile* out);
@@ -162,6 +164,17 @@ int trpa_batch_upload(trpa_ctx* ctx, const trpa_segment* segs, uint32_t n_segs, 
                       uint32_t n_cands);
 int trpa_batch_run(trpa_ctx* ctx);
 int trpa_batch_download(trpa_ctx* ctx, trpa_result* out);
+
+/* Multi-GPU (taxator.cpp:181-210 parallelises over record sets only): segments are independent, so a batch is cut
+ * into `world` contiguous shards, one per GPU / context, and the fixed-size result records are concatenated in
+ * shard order.  Host-only helper, no GPU needed: bounds[0..world] = segment indices of the cuts, balanced by the
+ * estimated DP work (1 + sum of span^2 over a segment's records).  A shard's segment table must be rebased
+ * (cand_begin -= segs[bounds[r]].cand_begin) before it is handed to trpa_predict_batch. */
+int trpa_shard_bounds(const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands, uint32_t n_cands,
+                      uint32_t world, uint32_t* bounds);
+/* Device address of the result table of the last trpa_batch_run (n_segs records, valid until the next upload):
+ * lets a multi-process driver gather shards GPU to GPU (NVLink) instead of through host memory. */
+int trpa_batch_results_dev(trpa_ctx* ctx, void** dev_ptr, uint32_t* n_segs);
 
 /* ---- the alignment-free placement models behind the same predict() interface ------------------ */
 /* DummyPredictionModel, LCASimplePredictionModel, MeganLCAPredictionModel, NBestLCAPredictionModel

@@ -1,10 +1,11 @@
 // C ABI of the B200-native RPA hot path (include/taxator_rpa_b200.h) + the per-round driver:
 //   decide kernel (one thread per query segment, machine.h) -> stage kernel (pack.cu)
-//   -> shape bucketing -> edit-distance / protein kernels (myers.cuh / protein.cu) -> decide ...
+//   -> shape bucketing -> edit-distance / protein kernels (myers3.cuh / protein2.cu) -> decide ...
 // There is no CPU fallback: every compute entry point needs a CUDA device.
 // Compile with --fmad=false (decision arithmetic must match the reference's IEEE float/double ops).
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -76,7 +77,8 @@ struct Store {
   DevBuf<u64> woff;
   DevBuf<u32> len;
   u32 max_len = 0;
-  void release() { planes.release(); nplane.release(); packed.release(); woff.release(); len.release(); n_seq = 0; alphabet = -1; }
+  std::vector<u32> h_len;   // host copy of the sequence lengths (upload validation)
+  void release() { planes.release(); nplane.release(); packed.release(); woff.release(); len.release(); n_seq = 0; alphabet = -1; h_len.clear(); }
 };
 
 struct EventPair { cudaEvent_t a, b; int kind; };
@@ -94,7 +96,6 @@ struct Pipe {
   DevBuf<u32> d_hist;         // kNumShapes counts + scatter cursors + kernel work cursors, then (banded path)
                               // kNumShapes x kNumCls duration-class counts and their scatter cursors
   DevBuf<uint2> d_buckets;    // kNumShapes {start,count}
-  DevBuf<u32> scratch;
   DevBuf<uint4> scratch3;     // banded kernel: wrap-around strip boundaries, one line per group slot
   DevBuf<unsigned long long> d_plan;  // [1..3] {word-blocks, retries, pairs} of myers3
   DevBuf<int2> scratch_aa;
@@ -160,7 +161,6 @@ struct trpa_ctx {
   u64 arena_units = 0;
   int band = 1;               // 1: Ukkonen band (exact), 0: full DP matrix
   int wedge = 1;              // 1: let the band narrow along the matrix where a certificate can prove it (exact)
-  int myers_version = 3;      // 3: banded rotating-strip kernel, 2: myers2 (A/B runs, TRPA_MYERS=2)
   // pipes: independent sub-batch pipelines whose rounds overlap on the GPU (pipe[0] runs on `stream`)
   static constexpr int kMaxPipes = 4;
   Pipe pipe[kMaxPipes];
@@ -193,28 +193,6 @@ __global__ void init_state_kernel(SegState* st, u32 n) {
   if (s < n) st[s].phase = PH_INIT;
 }
 
-// exact shape of every pair of the round (needs the staged N flags) + histogram
-__global__ void classify_kernel(PairDesc* pairs, u32 n, const SeqDesc* descs, u32* hist, int lmin) {
-  for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    PairDesc p = pairs[k];
-    const SeqDesc a = descs[p.a], b = descs[p.b];
-    const u32 m = a.len < b.len ? a.len : b.len;
-    const int shape = choose_shape((m + 31u) >> 5, (a.flags | b.flags) & 1u, lmin);
-    pairs[k].pad = (u32)shape;
-    atomicAdd(&hist[shape], 1u);
-  }
-}
-__global__ void scan_kernel(u32* hist, uint2* buckets) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    u32 acc = 0;
-    for (int s = 0; s < kNumShapes; ++s) {
-      const u32 c = hist[s];
-      buckets[s] = make_uint2(acc, c);
-      hist[kNumShapes + s] = acc;  // scatter cursor
-      acc += c;
-    }
-  }
-}
 // banded path: buckets by shape and, inside a shape, by duration class, longest first (the persistent groups pull
 // pairs in this order: longest-processing-time-first keeps the tail of a launch short)
 constexpr u32 kHistWords = 3u * kNumShapes + 2u * kNumShapes * kNumCls;
@@ -242,14 +220,6 @@ __global__ void scatter3_kernel(const PairDesc* pairs, u32 n, u32* hist, PairDes
     sorted[pos] = p;
   }
 }
-__global__ void scatter_kernel(const PairDesc* pairs, u32 n, u32* hist, PairDesc* sorted) {
-  for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const PairDesc p = pairs[k];
-    const u32 pos = atomicAdd(&hist[kNumShapes + (p.pad & 0xffu)], 1u);   // pad: shape | k0 << 8
-    sorted[pos] = p;
-  }
-}
-
 // SortFilter on the device (core/src/alignmentsfilter.hh:171-190: stable sort, descending (score,
 // identities)): one warp per segment ranks every record against all others of its segment; the
 // original position breaks ties, which is exactly what a stable sort does.  raw -> sorted table.
@@ -332,7 +302,7 @@ int Pipe::init(cudaStream_t user_stream) {
 }
 void Pipe::release() {
   if (stream) cudaStreamSynchronize(stream);
-  d_counters.release(); d_hist.release(); d_buckets.release(); scratch.release(); scratch3.release();
+  d_counters.release(); d_hist.release(); d_buckets.release(); scratch3.release();
   d_plan.release(); scratch_aa.release();
   for (auto& e : ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   ev_pool.clear();
@@ -350,50 +320,7 @@ void Pipe::release() {
 
 static Taxonomy dev_tax(trpa_ctx* c) { return Taxonomy{c->t_parent.p, c->t_left.p, c->t_right.p, c->t_depth.p, c->root}; }
 
-// Shared by the pipeline and the low-level API.
-// bucket_pairs: exact kernel shape of every pair (length class, has-N, and -- when the round is too
-// small to fill the GPU -- more lanes per pair), counting sort by shape on the device; the per-shape
-// counts come back to the host (h_hist) so that only non-empty shapes are launched.
-static int bucket_pairs(trpa_ctx* c, Pipe& P, PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, PairDesc* sorted, u32* h_hist) {
-  CK(cudaMemsetAsync(P.d_hist.p, 0, sizeof(u32) * 3 * kNumShapes, P.stream));
-  const u32 blocks = std::min<u32>((n_pairs + 255) / 256, 148 * 8);
-  const int lmin = lmin_for(n_pairs, (u32)c->num_sms * 16u * 32u);
-  classify_kernel<<<blocks, 256, 0, P.stream>>>(pairs, n_pairs, descs, P.d_hist.p, lmin);
-  scan_kernel<<<1, 32, 0, P.stream>>>(P.d_hist.p, P.d_buckets.p);
-  scatter_kernel<<<blocks, 256, 0, P.stream>>>(pairs, n_pairs, P.d_hist.p, sorted);
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(h_hist, P.d_hist.p, sizeof(u32) * kNumShapes, cudaMemcpyDeviceToHost, P.stream));
-  return 0;   // asynchronous: synchronise P.stream before reading h_hist
-}
-
-// one launch per non-empty shape over the shape-sorted pair list
-static int launch_myers_shapes(trpa_ctx* c, Pipe& P, const u32* h_hist, const PairDesc* sorted, const SeqDesc* descs,
-                               const uint2* planes, const u32* nplane, int* out, u32 max_len) {
-  const u32 stride = (max_len + 31) / 32 + 1;
-  // work cursors of the persistent kernels (one per shape)
-  CK(cudaMemsetAsync(P.d_hist.p + 2 * kNumShapes, 0, sizeof(u32) * kNumShapes, P.stream));
-  u32 start = 0;
-  for (int shape = 0; shape < kNumShapes; ++shape) {
-    const u32 cnt = h_hist[shape];
-    if (!cnt) continue;
-    const int L = 1 << shape_lidx(shape);
-    const int W = shape_W(shape_widx(shape));
-    u32* scr = nullptr;
-    if (L == 32 && (u64)stride * 32 > (u64)32 * W * 32) {  // some pattern may need >1 strip
-      // kernels of one stream run back to back, so one scratch area serves all shapes
-      if (P.scratch.ensure((size_t)myers_group_slots(shape, cnt) * 3 * stride)) return TRPA_ERR_NOMEM;
-      scr = P.scratch.p;
-    }
-    CK(launch_myers(shape, sorted + start, cnt, descs, planes, nplane, out, scr, stride, nullptr,
-                    P.d_hist.p + 2 * kNumShapes + shape, P.stream));
-    c->prof.launches_edit_distance++;
-    start += cnt;
-  }
-  return 0;
-}
-
-
-// ---- banded path: plan (threshold + shape per pair), counting sort by shape, one launch per shape
+// ---- plan (threshold + shape per pair), counting sort by shape, one launch per shape
 static int bucket_pairs3(trpa_ctx* c, Pipe& P, PairDesc* pairs, u32 n_pairs, const SeqDesc* descs, const uint2* planes,
                          const u32* nplane, PairDesc* sorted, u32* h_hist) {
   CK(cudaMemsetAsync(P.d_hist.p, 0, sizeof(u32) * kHistWords, P.stream));
@@ -526,7 +453,6 @@ trpa_ctx* trpa_create(int device, void* cuda_stream) {
   if (cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->num_sms <= 0) c->num_sms = 148;
   if (const char* e = getenv("TRPA_BAND")) c->band = e[0] != '0';
   if (const char* e = getenv("TRPA_WEDGE")) c->wedge = e[0] != '0';
-  if (const char* e = getenv("TRPA_MYERS")) c->myers_version = e[0] == '2' ? 2 : 3;
   if (const char* e = getenv("TRPA_PIPES")) c->n_pipes = std::max(1, std::min((int)trpa_ctx::kMaxPipes, atoi(e)));
   return c;
 }
@@ -580,7 +506,6 @@ int trpa_set_tuning(trpa_ctx* c, const char* key, int64_t value) {
   else if (k == "cost_setup") c->plan.setup = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
   else if (k == "cost_setup_w") c->plan.setup_w = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 16));
   else if (k == "plan_lanes") c->plan_lanes = value < 0 ? 0u : (u32)std::min<int64_t>(value, 1 << 30);
-  else if (k == "myers_version") c->myers_version = value == 2 ? 2 : 3;
   else if (k == "wedge") c->wedge = value < 0 ? 0 : (value > 2 ? 2 : (int)value);   // 2: test hook, see plan_kernel
   else if (k == "la_cap") c->la_cap = (u32)std::max<int64_t>(1, value);
   else if (k == "la_max") c->la_max = (u32)std::max<int64_t>(0, std::min<int64_t>(64, value));
@@ -658,6 +583,7 @@ int trpa_load_store(trpa_ctx* c, int store, int alphabet, const char* chars, con
   }
   d_chars.release(); d_off.release();
   S.alphabet = alphabet; S.n_seq = n_seq; S.n_words = words; S.max_len = maxlen;
+  S.h_len.assign(len, len + n_seq);
   c->batch_ready = false;
   return 0;
 }
@@ -728,6 +654,7 @@ int trpa_load_store_packed(trpa_ctx* c, int store, int alphabet, const uint64_t*
   }
   CK(cudaStreamSynchronize(c->stream));
   S.alphabet = alphabet; S.n_seq = n_seq; S.n_words = n_words; S.max_len = maxlen;
+  S.h_len.assign(len, len + n_seq);
   c->batch_ready = false;
   return 0;
 }
@@ -743,14 +670,26 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
   if (Q.alphabet < 0 || R.alphabet < 0 || Q.alphabet != R.alphabet) { set_error("query/reference stores not loaded or of different alphabets"); return TRPA_ERR_STATE; }
   if ((u64)n_segs + n_cands >= 0xfffffff0ull) { set_error("batch too large"); return TRPA_ERR_ARG; }
   const bool protein = Q.alphabet == TRPA_ALPHA_AA;
-  // validate the segment table (the reference throws SequenceNotFound / TaxonNotFound at parse time)
-  for (u32 s = 0; s < n_segs; ++s) {
-    if ((u64)segs[s].cand_begin + segs[s].cand_count > n_cands) { set_error("segment candidate range out of bounds"); return TRPA_ERR_ARG; }
-    if (segs[s].cand_count && segs[s].query_seq >= Q.n_seq) { set_error("segment query ordinal out of range"); return TRPA_ERR_ARG; }
+  c->batch_ready = false;   // a failed upload must not leave the previous batch's plan runnable over new tables
+  // validate the segment table (the reference throws SequenceNotFound / TaxonNotFound at parse time).
+  // Contract (include/taxator_rpa_b200.h): record sets are contiguous and in order, segs[s].cand_begin ==
+  // sum of the earlier cand_counts -- the per-candidate work arrays and the round queues are laid out by it.
+  {
+    u64 expect = 0;
+    for (u32 s = 0; s < n_segs; ++s) {
+      if (segs[s].cand_begin != expect || expect + segs[s].cand_count > n_cands) {
+        set_error("segment table: candidate ranges must be contiguous, ascending and inside the candidate table");
+        return TRPA_ERR_ARG;
+      }
+      expect += segs[s].cand_count;
+      if (segs[s].cand_count && segs[s].query_seq >= Q.n_seq) { set_error("segment query ordinal out of range"); return TRPA_ERR_ARG; }
+    }
   }
   // The raw tables go to the device straight from the caller's buffers (a DMA when they are pinned)
   // while the host makes its one validation pass over them; SortFilter then runs on the device.
   if (c->d_segs.ensure(n_segs + 1) || c->d_cands.ensure(n_cands + 1) || c->d_cands_raw.ensure(n_cands + 1)) return TRPA_ERR_NOMEM;
+  // from here on the stream reads the caller's buffers: every return synchronises first
+  struct SyncGuard { cudaStream_t st; ~SyncGuard() { cudaStreamSynchronize(st); } } sync_guard{c->stream};
   CK(cudaMemcpyAsync(c->d_segs.p, segs, sizeof(trpa_segment) * n_segs, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_cands_raw.p, cands, sizeof(trpa_candidate) * n_cands, cudaMemcpyHostToDevice, c->stream));
   if (n_segs) {
@@ -764,13 +703,18 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
     // assert(!qgroup.empty()) in the reference (hh:563); reject it instead of guessing.
     const float factor = 1. - c->toppercent;
     const u32 nseq = R.n_seq, nnodes = c->n_nodes;
-    int bad[6] = {0, 0, 0, 0, 0, 0};
+    const u32* qlen = Q.h_len.data();
+    // first bad record in table order wins (one slot per worker block, reduced afterwards)
+    struct Bad { size_t seg; int code; };
+    std::mutex bad_mutex;
+    Bad first_bad{~(size_t)0, 0};
     parallel_blocks(n_segs, [&](size_t b, size_t e) {
       int code = 0;
+      size_t at = 0;
       for (size_t s = b; s < e && !code; ++s) {
         const trpa_segment sg = segs[s];
         const trpa_candidate* rc = cands + sg.cand_begin;
-        u32 ms = 0;
+        u32 ms = 0, qmin = 0xffffffffu;
         float best = sg.cand_count ? rc[0].score : 0.f;
         for (u32 k = 0; k < sg.cand_count; ++k) {
           const trpa_candidate& x = rc[k];
@@ -780,25 +724,30 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
           else if (x.rstart == 0 || x.rstop == 0) code = 4;
           if (code) break;
           best = std::max(best, x.score);
+          qmin = std::min(qmin, x.qstart);
           const u64 span = (x.rstart <= x.rstop ? (u64)x.rstop - x.rstart : (u64)x.rstart - x.rstop) + 1;
           ms = (u32)std::min<u64>(0xffffffffull, std::max<u64>(ms, span));
         }
-        if (code) break;
-        if (sg.cand_count >= 2 && !(best >= factor * best)) { code = 5; break; }
+        if (!code && sg.cand_count >= 2 && !(best >= factor * best)) code = 5;
+        // the reference fetches the query range of every n >= 2 record set (hh:415) and its in-memory query
+        // store throws SequenceRangeError when the range starts beyond the sequence (sequencestorage.hh:118)
+        if (!code && sg.cand_count >= 2 && qmin > qlen[sg.query_seq]) code = 6;
+        if (code) { at = s; break; }
         maxspan[s] = ms;
         bound[s] = segment_arena_bound(sg, cands, protein);
       }
-      if (code) bad[code] = 1;
+      if (code) {
+        std::lock_guard<std::mutex> lock(bad_mutex);
+        if (at < first_bad.seg) first_bad = Bad{at, code};
+      }
     });
-    const char* msg = bad[1] ? "candidate reference ordinal out of range"
-                    : bad[2] ? "candidate taxon node out of range"
-                    : bad[3] ? "candidate query range invalid (qstart must be >= 1 and <= qstop)"
-                    : bad[4] ? "candidate reference coordinates are 1-based"
-                    : bad[5] ? "segment with negative best alignment score: undefined in the reference (hh:563)" : nullptr;
-    if (msg) {
-      cudaStreamSynchronize(c->stream);   // the copies read the caller's buffers
+    static const char* const kMsg[7] = {nullptr, "candidate reference ordinal out of range", "candidate taxon node out of range",
+      "candidate query range invalid (qstart must be >= 1 and <= qstop)", "candidate reference coordinates are 1-based",
+      "segment with negative best alignment score: undefined in the reference (hh:563)",
+      "segment query range starts beyond the query sequence (SequenceRangeError, sequencestorage.hh:118)"};
+    if (first_bad.code) {
       cudaGetLastError();
-      set_error(msg);
+      set_error(std::string(kMsg[first_bad.code]) + " (segment " + std::to_string(first_bad.seg) + ")");
       return TRPA_ERR_ARG;
     }
   }
@@ -913,7 +862,6 @@ static int step_pipe(trpa_ctx* c, Pipe& P, int pipe_index, size_t& next_chunk, c
   const Store& Q = c->store[TRPA_STORE_QUERY];
   const Store& R = c->store[TRPA_STORE_REF];
   const bool protein = Q.alphabet == TRPA_ALPHA_AA;
-  const bool v3 = c->myers_version == 3;
   CK(cudaStreamSynchronize(P.stream));
   harvest_events(c, P);
   if (P.state == PS_WAIT_DECIDE) {
@@ -933,7 +881,7 @@ static int step_pipe(trpa_ctx* c, Pipe& P, int pipe_index, size_t& next_chunk, c
       // 1 byte written per residue)
       const u64 units = P.h_counters[CN_ARENA];
       c->prof.bytes_stage += protein ? (units * 13) / 8 : units * 32;
-      if (!protein && v3) { const int rc = harvest_band_stats(c, P); if (rc) return rc; }
+      if (!protein) { const int rc = harvest_band_stats(c, P); if (rc) return rc; }
       return start_chunk(c, P, pipe_index, next_chunk, base);
     }
     P.n_pairs = n_pairs;
@@ -966,11 +914,10 @@ static int step_pipe(trpa_ctx* c, Pipe& P, int pipe_index, size_t& next_chunk, c
     // --- plan: threshold + shape of every pair, counting sort by shape, histogram to the host
     ev = begin_event(P, EV_OTHER);
     u32* h_hist = P.h_counters + kNumCounters;
-    const int rc = v3 ? bucket_pairs3(c, P, P.pairs, n_pairs, c->d_descs.p, c->arena_planes.p, c->arena_n.p, P.sorted, h_hist)
-                      : bucket_pairs(c, P, P.pairs, n_pairs, c->d_descs.p, P.sorted, h_hist);
+    const int rc = bucket_pairs3(c, P, P.pairs, n_pairs, c->d_descs.p, c->arena_planes.p, c->arena_n.p, P.sorted, h_hist);
     if (rc) return rc;
     end_event(P, ev);
-    c->prof.launches_other += v3 ? 3 : 3;
+    c->prof.launches_other += 3;
     P.state = PS_WAIT_PLAN;
     return 0;
   }
@@ -978,10 +925,8 @@ static int step_pipe(trpa_ctx* c, Pipe& P, int pipe_index, size_t& next_chunk, c
     // --- align: one persistent launch per non-empty shape
     const u32* h_hist = P.h_counters + kNumCounters;
     const int ev = begin_event(P, EV_MYERS);
-    const int rc = v3 ? launch_myers_shapes3(c, P, h_hist, P.sorted, c->d_descs.p, c->arena_planes.p, c->arena_n.p, c->arena_codes.p,
-                                             c->d_res.p, c->max_stage_len)
-                      : launch_myers_shapes(c, P, h_hist, P.sorted, c->d_descs.p, c->arena_planes.p, c->arena_n.p,
-                                            c->d_res.p, c->max_stage_len);
+    const int rc = launch_myers_shapes3(c, P, h_hist, P.sorted, c->d_descs.p, c->arena_planes.p, c->arena_n.p, c->arena_codes.p,
+                                        c->d_res.p, c->max_stage_len);
     if (rc) return rc;
     end_event(P, ev);
     // reset the per-round counters, keep the arena cursor
@@ -1062,6 +1007,13 @@ int trpa_batch_download(trpa_ctx* c, trpa_result* out) {
   return 0;
 }
 
+int trpa_batch_results_dev(trpa_ctx* c, void** dev_ptr, uint32_t* n_segs) {
+  if (!c || !dev_ptr || !n_segs) { set_error("bad arguments"); return TRPA_ERR_ARG; }
+  if (!c->batch_ready) { set_error("no batch uploaded"); return TRPA_ERR_STATE; }
+  *dev_ptr = c->d_results.p; *n_segs = c->n_segs;
+  return 0;
+}
+
 int trpa_predict_batch(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands,
                        uint32_t n_cands, trpa_result* out) {
   int rc = trpa_batch_upload(c, segs, n_segs, cands, n_cands);
@@ -1121,10 +1073,8 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   for (u32 k = 0; k < n_pairs; ++k) hp[k] = PairDesc{pair_a[k], pair_b[k], k, 0, 0};
   CK(cudaMemcpyAsync(d_pairs.p, hp.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, c->stream));
   std::vector<u32> h_hist(kNumShapes, 0);
-  const bool v3 = c->myers_version == 3;
   Pipe& P = c->pipe[0];
-  rc = v3 ? bucket_pairs3(c, P, d_pairs.p, n_pairs, d_sd.p, planes.p, nplane.p, d_sorted.p, P.h_counters + kNumCounters)
-          : bucket_pairs(c, P, d_pairs.p, n_pairs, d_sd.p, d_sorted.p, P.h_counters + kNumCounters);
+  rc = bucket_pairs3(c, P, d_pairs.p, n_pairs, d_sd.p, planes.p, nplane.p, d_sorted.p, P.h_counters + kNumCounters);
   if (rc) return rc;
   CK(cudaStreamSynchronize(P.stream));
   memcpy(h_hist.data(), P.h_counters + kNumCounters, sizeof(u32) * kNumShapes);
@@ -1133,14 +1083,12 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   if (repeat < 1) repeat = 1;
   // one untimed pass when timing is requested
   if (kernel_ms && repeat > 1) {
-    rc = v3 ? launch_myers_shapes3(c, P, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, codes.p, d_out.p, max_len)
-            : launch_myers_shapes(c, P, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
+    rc = launch_myers_shapes3(c, P, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, codes.p, d_out.p, max_len);
     if (rc) return rc;
   }
   CK(cudaEventRecord(e0, c->stream));
   for (int r = 0; r < repeat; ++r) {
-    rc = v3 ? launch_myers_shapes3(c, P, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, codes.p, d_out.p, max_len)
-            : launch_myers_shapes(c, P, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, d_out.p, max_len);
+    rc = launch_myers_shapes3(c, P, h_hist.data(), d_sorted.p, d_sd.p, planes.p, nplane.p, codes.p, d_out.p, max_len);
     if (rc) return rc;
   }
   CK(cudaEventRecord(e1, c->stream));
@@ -1150,7 +1098,7 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   CK(cudaEventElapsedTime(&ms, e0, e1));
   if (kernel_ms) *kernel_ms = ms / repeat;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  if (v3) { rc = harvest_band_stats(c, P); if (rc) return rc; }
+  rc = harvest_band_stats(c, P); if (rc) return rc;
   d_chars.release(); d_off.release(); d_sd.release(); planes.release(); codes.release(); nplane.release(); d_pairs.release();
   d_sorted.release(); d_out.release(); d_cnt.release(); d_flags.release();
   return 0;
@@ -1315,6 +1263,36 @@ int trpa_predict_lca_batch(trpa_ctx* c, const trpa_lca_params* pp, const trpa_se
   if (kernel_ms) *kernel_ms = ms / repeat;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   c->prof.launches_other += (u64)repeat;
+  return 0;
+}
+
+// Host-only helper (no GPU work): where to cut a segment table into `world` contiguous shards of about equal
+// DP work.  weight(segment) = 1 + sum over its records of span^2 (span = reference range of the record): the
+// number of realignments grows with the record count and each costs about |A| * |B| ~ span^2 cells.
+int trpa_shard_bounds(const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands, uint32_t n_cands,
+                      uint32_t world, uint32_t* bounds) {
+  if (!bounds || world == 0 || (n_segs && !segs) || (n_cands && !cands)) { set_error("bad arguments"); return TRPA_ERR_ARG; }
+  std::vector<u64> w(n_segs);
+  unsigned __int128 total = 0;
+  for (u32 s = 0; s < n_segs; ++s) {
+    if ((u64)segs[s].cand_begin + segs[s].cand_count > n_cands) { set_error("segment candidate range out of bounds"); return TRPA_ERR_ARG; }
+    u64 acc = 1;
+    const trpa_candidate* rc = cands + segs[s].cand_begin;
+    for (u32 k = 0; k < segs[s].cand_count; ++k) {
+      const u64 span = (rc[k].rstart <= rc[k].rstop ? (u64)rc[k].rstop - rc[k].rstart : (u64)rc[k].rstart - rc[k].rstop) + 1;
+      acc += span * span;   // span < 2^32: no overflow of the square; the sum saturates far beyond any real table
+    }
+    w[s] = acc;
+    total += acc;
+  }
+  bounds[0] = 0;
+  u32 r = 1;
+  unsigned __int128 acc = 0;
+  for (u32 s = 0; s < n_segs && r < world; ++s) {
+    acc += w[s];
+    while (r < world && acc * world >= total * r) bounds[r++] = s + 1;
+  }
+  while (r <= world) bounds[r++] = n_segs;
   return 0;
 }
 

@@ -6,14 +6,6 @@
 
 namespace trpa {
 
-// edit distance: pairs[0..count) all of one shape (shapes.h); scratch only for multi-strip pairs
-// bucket (nullable): device {start,count} of the shape inside pairs; count is then the grid bound
-// cursor: zeroed device counter of this launch (persistent kernel work fetch)
-cudaError_t launch_myers(int shape, const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint2* planes,
-                         const u32* nplane, int* out, u32* scratch, u32 scratch_stride, const uint2* bucket,
-                         u32* cursor, cudaStream_t stream);
-u32 myers_group_slots(int shape, u32 count);
-
 // banded edit distance (myers3.cuh).  launch_plan: initial threshold k0 + shape of every pair of the
 // round (PairDesc.pad: hint on entry; bits 0..7 shape, 8..31 k0 on exit) and the per-shape histogram.
 // band: 0 = full matrix, 1 = band, > 1 = band with that forced initial threshold (test hook).

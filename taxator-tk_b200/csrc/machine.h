@@ -175,7 +175,9 @@ struct Machine {
   }
   // segment i <-> segment j: triangle inequality over the query, exact query distances where known.
   // Bit 31 (kHintIsBound): both query distances are exact edit distances of the very strings the pair
-  // aligns, so the sum is a true upper bound and the planner adds no safety margin.
+  // aligns, so the sum is a true upper bound and the planner adds no safety margin.  CF_P0_ALIGNED marks
+  // exactly the records whose qd[] is such a distance: pass 2 clears it when it overwrites qd[i] with the
+  // distance to an outgroup anchor (hh:785) and sets it when it realigns an anchor against the query.
   TRPA_HD uint32_t hint_pair(uint32_t i, uint32_t j) const {
     if (B.protein) return 0u;
     const bool xi = qd[i] != FLT_MAX && (fl[i] & CF_P0_ALIGNED), xj = qd[j] != FLT_MAX && (fl[j] & CF_P0_ALIGNED);
@@ -432,7 +434,8 @@ struct Machine {
       read_alignment(S.cbeg + S.i, desc_cand(S.i), desc_cand(S.anchor), dist, sim);
       count_cells(desc_cand(S.i), desc_cand(S.anchor));
       ++S.c2;
-      qd[S.i] = dist;
+      qd[S.i] = dist;              // hh:785: no longer a distance to the query
+      fl[S.i] &= ~CF_P0_ALIGNED;   // ... so hint_pair must not treat it as one
       resume_p2 = true;
       goto p2_loop;
     }
@@ -601,6 +604,7 @@ struct Machine {
               count_cells(desc_cand(i), desc_cand(anchor));
               ++S.c2;
               qd[i] = dist;
+              fl[i] &= ~CF_P0_ALIGNED;
             } else {
               stage_candidate(anchor);
               stage_candidate(i);
@@ -624,6 +628,7 @@ struct Machine {
               count_cells(desc_cand(anchor), s);
               const float sim = s2 < qsim[anchor] ? qsim[anchor] : s2;  // std::max(s2, qsim[anchor])
               qd[anchor] = d2; qsim[anchor] = sim;
+              fl[anchor] |= CF_P0_ALIGNED;   // an exact query distance again
               qdist_ex = d2 * S.bandfactor_max;
               ++S.c2;
             } else if (qd[anchor] == FLT_MAX) {

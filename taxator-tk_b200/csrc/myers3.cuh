@@ -1,4 +1,4 @@
-// Third-generation edit-distance kernel: the same integer as myers.cuh / myers2.cuh / hh:150, but
+// Edit-distance kernel: the same integer as -globalAlignmentScore(.., MyersBitVector()) (hh:150), but
 // only the cells inside an Ukkonen band are computed (exact: see below), and the pattern strips of
 // a pair ROTATE over the lanes of its group so that a band of any width keeps every lane busy.
 //
@@ -32,7 +32,7 @@
 //    cert >= v proves that no such path beats v; otherwise the pair is run again with the plain band.
 // scripts/band_model.py is an executable model of exactly this schedule (checked against a plain DP).
 #pragma once
-#include "myers2.cuh"
+#include "bitvec.cuh"
 #include "shapes.h"
 
 namespace trpa {
@@ -75,7 +75,7 @@ __device__ __forceinline__ void sts_u4(u32 addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// One DP column for the W words of a lane (cf. myers2_column).  The carry into the strip's adder is the
+// One DP column for the W words of a lane .  The carry into the strip's adder is the
 // HN bit handed down from the row above: the exact carry of the strip above only matters where
 // Eq = VN = 0 in bit 0, and there it equals that bit (Myers' block formulation: hin < 0 <=> Eq |= 1),
 // so no carry word travels between strips.

@@ -123,12 +123,6 @@ cudaError_t launch_protein2(const PairDesc* pairs, u32 count, const SeqDesc* seq
                             int2* out2, int2* scratch, u32 scratch_stride, u32 max_len, cudaStream_t stream);
 int protein2_max_len();
 
-static bool protein_v1_only() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("TRPA_PROTEIN_V1"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
-
 // max_len: longest staged sequence of the launch (decides whether the 32-bit fallback kernel runs)
 cudaError_t launch_protein(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,
                            int2* out2, int2* scratch, u32 scratch_stride, u32 max_len, cudaStream_t stream) {
@@ -136,10 +130,6 @@ cudaError_t launch_protein(const PairDesc* pairs, u32 count, const SeqDesc* seqs
   cudaError_t e = ensure_table();
   if (e != cudaSuccess) return e;
   const u32 blocks = (count + 3) / 4;
-  if (protein_v1_only()) {
-    protein_kernel<<<blocks, 128, 0, stream>>>(pairs, count, seqs, residues, out2, scratch, scratch_stride, -1);
-    return cudaGetLastError();
-  }
   e = launch_protein2(pairs, count, seqs, residues, out2, scratch, scratch_stride, max_len, stream);
   if (e != cudaSuccess) return e;
   if ((int)max_len > protein2_max_len()) {

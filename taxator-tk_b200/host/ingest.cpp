@@ -77,6 +77,7 @@ inline bool parse_u32(const char* b, const char* e, uint32_t& v) {
 template <class T>
 inline bool parse_fp(const char* b, const char* e, T& v) {
   if (b == e) return false;
+  if (*b == '+' && e - b > 1 && b[1] != '-' && b[1] != '+') ++b;   // lexical_cast accepts an explicit plus sign, from_chars does not
   auto r = std::from_chars(b, e, v);
   return r.ec == std::errc() && r.ptr == e;
 }

@@ -23,14 +23,22 @@ static void split_fields(const std::string& s, size_t begin, std::vector<std::st
 }
 
 static uint32_t to_u32(const std::string& s, const char* what) {
-  if (s.empty() || s[0] == '-' || s[0] == '+') throw ParsingError(std::string("bad record: ") + what);
+  // boost::lexical_cast<unsigned>: digits only (no sign handled here, no leading blanks)
+  if (s.empty() || s[0] < '0' || s[0] > '9') throw ParsingError(std::string("bad record: ") + what);
   errno = 0;
   char* end = nullptr;
   unsigned long long v = strtoull(s.c_str(), &end, 10);
   if (errno || *end != '\0' || v > 0xffffffffull) throw ParsingError(std::string("bad record: ") + what);
   return (uint32_t)v;
 }
+// boost::lexical_cast<float/double> accepts neither leading blanks nor hexadecimal floats (strtof would)
+static bool plain_decimal(const std::string& s) {
+  if (s.empty() || isspace((unsigned char)s[0])) return false;
+  const size_t k = (s[0] == '-' || s[0] == '+') ? 1 : 0;
+  return !(s.size() > k + 1 && s[k] == '0' && (s[k + 1] == 'x' || s[k + 1] == 'X'));
+}
 static float to_float(const std::string& s, const char* what) {
+  if (!plain_decimal(s)) throw ParsingError(std::string("bad record: ") + what);
   errno = 0;
   char* end = nullptr;
   float v = strtof(s.c_str(), &end);
@@ -38,6 +46,7 @@ static float to_float(const std::string& s, const char* what) {
   return v;
 }
 static double to_double(const std::string& s, const char* what) {
+  if (!plain_decimal(s)) throw ParsingError(std::string("bad record: ") + what);
   char* end = nullptr;
   double v = strtod(s.c_str(), &end);
   if (s.empty() || *end != '\0') throw ParsingError(std::string("bad record: ") + what);

@@ -145,19 +145,12 @@ void RPAPredictionModelGPU::predictFlat(const trpa_segment* segs, uint32_t n_seg
                                         uint32_t n_cands, trpa_result* res) {
   const size_t n = n_segs;
   if (!n) return;
-  // shard contiguous segment ranges over the GPUs, balanced by candidate count; no collective
+  // shard contiguous segment ranges over the GPUs, balanced by the estimated DP work (trpa_shard_bounds:
+  // 1 + sum of span^2 per segment -- the same cuts python/shard.py and bench.py make); no collective
   const size_t G = std::min(ctx_.size(), std::max<size_t>(1, n));
-  std::vector<size_t> cut(G + 1, n);
-  cut[0] = 0;
-  {
-    const uint64_t total = (uint64_t)n_cands + n;
-    size_t g = 1;
-    uint64_t acc = 0;
-    for (size_t i = 0; i < n && g < G; ++i) {
-      acc += segs[i].cand_count + 1;
-      if (acc * G >= total * g) cut[g++] = i + 1;
-    }
-  }
+  std::vector<uint32_t> cut(G + 1, n_segs);
+  if (trpa_shard_bounds(segs, n_segs, cands, n_cands, (uint32_t)G, cut.data()))
+    throw TaxatorError(std::string("sharding failed: ") + trpa_last_error());
   std::vector<std::string> errors(G);
   if (G == 1) {
     if (trpa_predict_batch(ctx_[0], segs, n_segs, cands, n_cands, res)) errors[0] = trpa_last_error();

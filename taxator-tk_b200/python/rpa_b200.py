@@ -47,7 +47,7 @@ EXPORTS = ["trpa_abi_version", "trpa_last_error", "trpa_create", "trpa_destroy",
            "trpa_set_arena_bytes", "trpa_set_lookahead", "trpa_set_band", "trpa_set_tuning", "trpa_profile_reset", "trpa_profile_get", "trpa_load_taxonomy", "trpa_load_store", "trpa_store_info", "trpa_export_store", "trpa_load_store_packed",
            "trpa_predict_batch", "trpa_batch_upload", "trpa_batch_run", "trpa_batch_download",
            "trpa_predict_lca_batch", "trpa_edit_distance_batch", "trpa_protein_align_batch", "trpa_fetch_segments", "trpa_lca_batch",
-           "trpa_int_alu_peak"]
+           "trpa_int_alu_peak", "trpa_shard_bounds", "trpa_batch_results_dev"]
 
 _lib = None
 
@@ -70,6 +70,20 @@ def lib():
 
 class TrpaError(RuntimeError):
     pass
+
+
+def shard_bounds(segs, cands, world):
+    """trpa_shard_bounds: world+1 segment indices cutting the table into shards of about equal DP work
+    (host-only helper of the library; needs no GPU)."""
+    L = lib()
+    segs = np.ascontiguousarray(segs, SEG_DTYPE); cands = np.ascontiguousarray(cands, CAND_DTYPE)
+    out = np.zeros(int(world) + 1, np.uint32)
+    rc = L.trpa_shard_bounds(segs.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(len(segs)),
+                             cands.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(len(cands)),
+                             ctypes.c_uint32(int(world)), out.ctypes.data_as(ctypes.c_void_p))
+    if rc != 0:
+        raise TrpaError("rc=%d: %s" % (rc, L.trpa_last_error().decode()))
+    return [int(x) for x in out]
 
 
 def _p(a):
@@ -164,6 +178,12 @@ class Context:
             out = np.zeros(self._n_segs, RESULT_DTYPE)
         self._ck(self.L.trpa_batch_download(self.h, _p(out)))
         return out
+
+    def batch_results_dev(self):
+        """(device pointer, n_segs) of the result table of the last batch_run (valid until the next upload)."""
+        ptr = ctypes.c_void_p(0); n = ctypes.c_uint32(0)
+        self._ck(self.L.trpa_batch_results_dev(self.h, ctypes.byref(ptr), ctypes.byref(n)))
+        return ptr.value, n.value
 
     def profile_reset(self):
         self._ck(self.L.trpa_profile_reset(self.h))

@@ -8,6 +8,47 @@ import gff3
 
 GOLDEN = os.path.join(ol.ROOT, "tests", "golden")
 CASES = json.load(open(os.path.join(GOLDEN, "cases.json")))
+try:
+    HEAVY = tuple(json.load(open(os.path.join(GOLDEN, "cases_meta.json")))["heavy"])
+except Exception:
+    HEAVY = ()
+
+
+def long_pair(seed, L, rate, indel, n_over_m=1.0):
+    """Deterministic long nucleotide pair (only the seed is stored in the fixtures): a = uniform ACGT of length
+    L; b = an independent window-free mutation of a (rate substitutions; if indel, a third of the events are
+    deletions and a third insertions), optionally extended by random bases to n_over_m * L."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    nt = np.frombuffer(b"ACGT", np.uint8)
+    a = nt[rng.integers(0, 4, L)]
+    r = rng.random(L)
+    b = a.copy()
+    sub = r < (rate / 3 if indel else rate)
+    b[sub] = nt[(np.searchsorted(nt, b[sub]) + rng.integers(1, 4, int(sub.sum()))) % 4]
+    if indel:
+        reps = np.ones(L, np.int64)
+        reps[(r >= rate / 3) & (r < 2 * rate / 3)] = 0
+        ins = (r >= 2 * rate / 3) & (r < rate)
+        reps[ins] = 2
+        b = np.repeat(b, reps)
+        pos = np.cumsum(reps)[ins] - 1
+        b[pos] = nt[rng.integers(0, 4, len(pos))]
+    extra = int(round(L * (n_over_m - 1.0)))
+    if extra > 0:
+        b = np.concatenate([b, nt[rng.integers(0, 4, extra)]])
+    return np.ascontiguousarray(a), np.ascontiguousarray(b)
+
+
+
+def long_pairs():
+    """[(a, b, distance computed by the real SeqAn)] of tests/golden/seqan_long_pairs.json."""
+    out = []
+    for spec in json.load(open(os.path.join(GOLDEN, "seqan_long_pairs.json"))):
+        a, b = long_pair(spec["seed"], spec["L"], spec["rate"], spec["indel"], spec["n_over_m"])
+        assert len(a) == spec["m"] and len(b) == spec["n"]
+        out.append((a, b, spec["dist"]))
+    return out
 
 
 def case_data(name):

@@ -62,3 +62,36 @@ def test_c2_full_size_execution_invariance(ctx):
         ctx.set_lookahead(-1)
         ctx.set_tuning("pipes", 1)
         ctx.set_arena_bytes(0)
+
+
+@pytest.mark.parametrize("workload,n_queries", [("c4", 6000), ("c5", 400)])
+def test_c4_c5_regime_band_wedge_vs_full_matrices(ctx, workload, n_queries):
+    """BASELINE.json configs[3] (mixed 0.5-20 kb) and configs[4] (10-50 kb reads, 5 % substitutions + 10 %
+    indels) on a sample: the planned band + certified wedge, the plain band and the full DP matrices give the
+    same placements, counters and cells -- the wedge certificate and the verify-and-widen loop at the lengths and
+    divergences where they matter."""
+    import bench
+    fd = bench.Flat(bench.make_data(workload, 20261017, n_queries=n_queries))
+    ctx.load_taxonomy(fd.parent, fd.left, fd.right, fd.depth, 0)
+    ctx.load_store(0, 0, fd.q_chars, fd.q_off, fd.q_len)
+    ctx.load_store(1, 0, fd.r_chars, fd.r_off, fd.r_len)
+    try:
+        ctx.profile_reset()
+        base = ctx.predict_batch(fd.segs, fd.cands)
+        prof = ctx.profile()
+        cells = int(base["cells"].sum())
+        assert (base["kind"] == 3).all() and cells > 0
+        assert 0 < prof["cells_edit_distance"] < 0.5 * cells
+        ctx.set_tuning("wedge", 0)
+        ctx.profile_reset()
+        plain = ctx.predict_batch(fd.segs, fd.cands)
+        assert ctx.profile()["wedge_failures"] == 0
+        assert _same(base, plain)
+        ctx.set_band(0)
+        ctx.profile_reset()
+        full = ctx.predict_batch(fd.segs, fd.cands)
+        assert ctx.profile()["cells_edit_distance"] >= cells
+        assert _same(base, full)
+    finally:
+        ctx.set_band(1)
+        ctx.set_tuning("wedge", 1)

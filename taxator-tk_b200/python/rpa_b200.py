@@ -164,6 +164,13 @@ class Context:
                                            ctypes.c_uint32(len(cands)), _p(out)))
         return out
 
+    def predict_batch_into(self, segs, cands, out):
+        """trpa_predict_batch with caller-owned (e.g. pinned) buffers; no copies on the Python side."""
+        assert segs.dtype == SEG_DTYPE and cands.dtype == CAND_DTYPE and out.dtype == RESULT_DTYPE and len(out) >= len(segs)
+        self._ck(self.L.trpa_predict_batch(self.h, _p(segs), ctypes.c_uint32(len(segs)), _p(cands),
+                                           ctypes.c_uint32(len(cands)), _p(out)))
+        return out[:len(segs)]
+
     def batch_upload(self, segs, cands):
         segs = np.ascontiguousarray(segs, SEG_DTYPE); cands = np.ascontiguousarray(cands, CAND_DTYPE)
         self._n_segs = len(segs)

@@ -383,14 +383,14 @@ def generate(cfg: SynthConfig, identity_fn=None) -> SynthData:
     return d
 
 
-def generate_fast(cfg: SynthConfig, block: int = 100) -> SynthData:
-    """Vectorised generator for benchmark-sized nucleotide configs (same SynthData layout).
+class FastReference:
+    """Taxonomy + refpack + block-resolution identity tables of generate_fast, built once from cfg.seed."""
+    pass
 
-    Differences from generate(): query windows start on `block` boundaries, candidate identities are
-    block-resolution ungapped identities of the source window (scaled by the query noise) -- they only
-    need to be plausible and tie-free, not exact -- and genomes are not truncated.  Substitution-only
-    queries (query_indel is ignored unless > 0, then a slower per-query path is used)."""
-    rng = np.random.default_rng(cfg.seed)
+
+def build_reference_fast(cfg: SynthConfig, rng, block: int = 100):
+    """First half of generate_fast: taxonomy, evolved genomes, the stored refpack and the cumulative block
+    identities between neighbouring genomes.  Returns (SynthData without queries, FastReference)."""
     alphabet = AA20 if cfg.protein else NT
     d = SynthData(cfg=cfg)
     counts = list(cfg.levels) + [cfg.n_genomes]
@@ -449,25 +449,37 @@ def generate_fast(cfg: SynthConfig, block: int = 100) -> SynthData:
             continue
         eq = (E[lo:hi] == E[lo + off:hi + off]).reshape(hi - lo, nb, block).sum(axis=2)
         cum[lo:hi, oi, 1:] = np.cumsum(eq, axis=1)
+    ref = FastReference()
+    ref.block, ref.G, ref.E, ref.is_rev, ref.cum, ref.K, ref.half, ref.n_g = block, G, E, is_rev, cum, K, half, n_g
+    return d, ref
 
-    nq = cfg.n_queries
-    Lq = (rng.integers(cfg.query_len[0], cfg.query_len[1] + 1, nq) // block) * block
-    Lq = np.clip(Lq, block, G)
+
+def draw_query_lengths(cfg: SynthConfig, ref, rng, nq):
+    """The first draw of generate_queries_fast on a fresh generator: the source-window lengths of nq queries."""
+    Lq = (rng.integers(cfg.query_len[0], cfg.query_len[1] + 1, nq) // ref.block) * ref.block
+    return np.clip(Lq, ref.block, ref.G)
+
+
+def generate_queries_fast(cfg: SynthConfig, ref, rng, nq):
+    """Second half of generate_fast: nq queries cut from the evolved genomes (+ noise) and their alignment
+    records.  Returns (q_seqs: list of uint8 arrays, rec: dict of record columns, rec["q"] local to this call)."""
+    alphabet = AA20 if cfg.protein else NT
+    block, G, E, is_rev, cum, K, half, n_g = ref.block, ref.G, ref.E, ref.is_rev, ref.cum, ref.K, ref.half, ref.n_g
+    Lq = draw_query_lengths(cfg, ref, rng, nq)
     g0 = rng.integers(0, n_g, nq)
     pblk = (rng.random(nq) * ((G - Lq) // block + 1)).astype(np.int64)
     p = pblk * block
-    d.q_names = ["Q%06d" % i for i in range(nq)]
-    d.q_seqs = []
+    q_seqs = []
     for i0 in range(0, nq, 4096):
         i1 = min(nq, i0 + 4096)
         for i in range(i0, i1):
             src = E[g0[i], p[i]:p[i] + Lq[i]]
-            d.q_seqs.append(src)
+            q_seqs.append(src)
     # substitutions, chunked and vectorised over the concatenation
     lens = Lq.astype(np.int64)
     for i0 in range(0, nq, 8192):
         i1 = min(nq, i0 + 8192)
-        cat = np.concatenate(d.q_seqs[i0:i1])
+        cat = np.concatenate(q_seqs[i0:i1])
         cat = _mutate_subst(rng, cat, cfg.query_sub, alphabet)
         o = 0
         for i in range(i0, i1):
@@ -475,8 +487,8 @@ def generate_fast(cfg: SynthConfig, block: int = 100) -> SynthData:
             o += lens[i]
             if cfg.query_indel > 0:
                 seg = _mutate_indel(rng, seg, cfg.query_indel, alphabet)
-            d.q_seqs[i] = np.ascontiguousarray(seg)
-    qlen_final = np.array([len(s) for s in d.q_seqs], dtype=np.int64)
+            q_seqs[i] = np.ascontiguousarray(seg)
+    qlen_final = np.array([len(s) for s in q_seqs], dtype=np.int64)
 
     # candidate genomes: window of K around g0, clipped to [0, n_g)
     lo = np.clip(g0 - half, 0, n_g - K)
@@ -527,14 +539,89 @@ def generate_fast(cfg: SynthConfig, block: int = 100) -> SynthData:
     qidx = np.broadcast_to(np.arange(nq)[:, None], (nq, K))
     ident_f = flat(ident)
     alnlen_f = flat(alnlen)
-    d.rec = {
+    rec = {
         "q": flat(qidx).astype(np.uint32), "qstart": flat(qs2).astype(np.uint32), "qstop": flat(qe2).astype(np.uint32),
         "r": flat(cand_g).astype(np.uint32), "rstart": flat(rstart).astype(np.uint32),
         "rstop": flat(rstop).astype(np.uint32),
         "score": (2.0 * ident_f - 3.0 * (alnlen_f - ident_f)).astype(np.float32),
         "ident": ident_f.astype(np.uint32), "alnlen": alnlen_f.astype(np.uint32),
     }
+    return q_seqs, rec
+
+
+def generate_fast(cfg: SynthConfig, block: int = 100) -> SynthData:
+    """Vectorised generator for benchmark-sized nucleotide configs (same SynthData layout).
+
+    Differences from generate(): query windows start on `block` boundaries, candidate identities are
+    block-resolution ungapped identities of the source window (scaled by the query noise) -- they only
+    need to be plausible and tie-free, not exact -- and genomes are not truncated.  Substitution-only
+    queries (query_indel is ignored unless > 0, then a slower per-query path is used)."""
+    rng = np.random.default_rng(cfg.seed)
+    d, ref = build_reference_fast(cfg, rng, block)
+    d.q_seqs, d.rec = generate_queries_fast(cfg, ref, rng, cfg.n_queries)
+    d.q_names = ["Q%06d" % i for i in range(cfg.n_queries)]
     return d
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Block-wise generation of very large batches (BASELINE.json configs[3] / [4] at full size): the batch is the
+# concatenation of fixed-size query blocks, block k drawn from its own generator (seed, k), over ONE refpack /
+# taxonomy drawn from the base seed.  The batch therefore does not depend on how many ranks generate it, a rank
+# only generates the blocks that overlap its shard, and blocks can be generated by worker processes.
+def block_rng(cfg: SynthConfig, k: int):
+    return np.random.default_rng([int(cfg.seed), 7919, int(k)])
+
+
+def block_query_lengths(cfg: SynthConfig, ref, n_blocks: int, block_queries: int):
+    """Source-window lengths of every query of the batch, block by block (cheap: one draw per block) -- the
+    work estimate n_cand * L^2 that cuts the batch into shards before anything else is generated."""
+    return np.concatenate([draw_query_lengths(cfg, ref, block_rng(cfg, k), block_queries) for k in range(n_blocks)])
+
+
+_BLOCK_STATE = {}
+
+
+def _block_worker(k):
+    cfg, ref, block_queries = _BLOCK_STATE["args"]
+    q_seqs, rec = generate_queries_fast(cfg, ref, block_rng(cfg, k), block_queries)
+    lens = np.array([len(s) for s in q_seqs], np.uint32)
+    return k, np.concatenate(q_seqs), lens, rec
+
+
+def generate_blocks(cfg: SynthConfig, d: SynthData, ref, block_ids, block_queries: int, workers: int = 1):
+    """Blocks `block_ids` of the batch.  Returns (q_chars, q_len, segs, cands) with query ordinals / candidate
+    offsets local to the returned range (block order).  workers > 1 forks worker processes -- call it before
+    CUDA is initialised in this process."""
+    block_ids = list(block_ids)
+    _BLOCK_STATE["args"] = (cfg, ref, block_queries)
+    if workers > 1 and len(block_ids) > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(workers, len(block_ids))) as pool:
+            parts = pool.map(_block_worker, block_ids, chunksize=1)
+    else:
+        parts = [_block_worker(k) for k in block_ids]
+    parts.sort(key=lambda x: x[0])
+    if not parts:
+        return np.zeros(0, np.uint8), np.zeros(0, np.uint32), np.zeros(0, SEG_DTYPE), np.zeros(0, CAND_DTYPE)
+    # one output buffer, parts released as they are copied (a shard of the 2M-segment batch is tens of GB)
+    chars = np.empty(sum(len(x[1]) for x in parts), np.uint8)
+    lens, segs, cands = [], [], []
+    qbase = cbase = cpos = 0
+    for i in range(len(parts)):
+        _, ch, ln, rec = parts[i]
+        parts[i] = None
+        chars[cpos:cpos + len(ch)] = ch
+        cpos += len(ch)
+        del ch
+        tmp = SynthData(cfg=cfg)
+        tmp.rec, tmp.ref_taxnode = rec, d.ref_taxnode
+        sg, cd = segments_fast(tmp)
+        sg["query_seq"] += qbase
+        sg["cand_begin"] += cbase
+        qbase += len(ln)
+        cbase += len(cd)
+        lens.append(ln); segs.append(sg); cands.append(cd)
+    return chars, np.concatenate(lens), np.concatenate(segs), np.concatenate(cands)
 
 
 def segments_fast(d: SynthData):

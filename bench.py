@@ -97,13 +97,21 @@ def emit(text):
     out.flush()
 
 
-def make_data(workload, seed, n_queries=None):
+def make_data(workload, seed, n_queries=None, rank=0):
+    """Rank 0: synth.generate_fast(seed).  Other ranks (weak scaling): the SAME refpack and taxonomy (drawn from
+    `seed`) with their own query block -- every rank then owns statistically the same work; with one seed per rank
+    the refpacks differ (tree shape, divergence) and the slowest rank's luck shows up as lost scaling efficiency."""
     w = WORKLOADS[workload]
     cfg = dict(w["cfg"])
     if n_queries is not None:
         cfg["n_queries"] = n_queries
     c = synth.SynthConfig(seed=seed, protein=w["protein"], **cfg)
-    return synth.generate_fast(c)
+    if rank == 0:
+        return synth.generate_fast(c)
+    d, ref = synth.build_reference_fast(c, np.random.default_rng(c.seed))
+    d.q_seqs, d.rec = synth.generate_queries_fast(c, ref, synth.block_rng(c, 1000003 + rank), c.n_queries)
+    d.q_names = ["Q%06d" % i for i in range(c.n_queries)]
+    return d
 
 
 class Flat:
@@ -232,7 +240,7 @@ def lca_bench(args, rank, local_rank, world):
     """the alignment-free models (megan-lca with the reference's defaults) on the record tables of
     C2 (100k segments x 50 records).  HBM-bound streaming kernel: 44 B read per record, 72 B per segment."""
     w = WORKLOADS["c2"]
-    d = make_data("c2", args.seed + rank, n_queries=args.segments)
+    d = make_data("c2", args.seed, n_queries=args.segments, rank=rank)
     segs, cands = synth.segments_fast(d)
     parent, left, right, depth = d.nested_set()
     n_seg, n_cand = len(segs), len(cands)
@@ -659,7 +667,7 @@ def main():
     # ---- synthetic data (CPU, before CUDA is initialised: the block generator forks worker processes).
     # Headline workload: every rank owns its own shard (weak scaling).
     t0 = time.time()
-    d = make_data(args.workload, args.seed + rank, n_queries=args.segments)
+    d = make_data(args.workload, args.seed, n_queries=args.segments, rank=rank)
     fd = Flat(d)
     n_seg, n_cand = len(fd.segs), len(fd.cands)
     t_gen = time.time() - t0

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TRPA_ABI_VERSION 6
+#define TRPA_ABI_VERSION 7
 
 #define TRPA_OK 0
 #define TRPA_ERR_CUDA (-1)
@@ -203,6 +203,56 @@ typedef struct trpa_lca_params {
 int trpa_predict_lca_batch(trpa_ctx* ctx, const trpa_lca_params* params, const trpa_segment* segs, uint32_t n_segs,
                            const trpa_candidate* cands, uint32_t n_cands, const double* evalue,
                            const uint8_t* node_unclassified, trpa_result* out, int repeat, double* kernel_ms);
+
+/* ---- downstream consensus: `binner` (core/binner.cpp:186-333, core/src/predictionranges.hh:122-266) -------------
+ * One call = one sample: all GFF3 prediction records of the sample, grouped by (globbed) sequence identifier.
+ * Step 1 (binner.cpp:213-281): per-taxon sample support = sum over records of the running maximum of the record's
+ * support from its lower node up to the root (uint32 sums), optional noise pruning of range ends whose sample
+ * support is below a minimum.  Step 2 (predictionranges.hh): per group, walk down from the root, keep the majority
+ * branch, place the group at the deepest node whose direct support reaches the threshold ("direct") or at the
+ * deepest node whose total support does ("fallback") -- with the reference's uint16 arithmetic
+ * (medium_unsigned_int, core/src/types.hh:35).  Optional per-rank identity constraints (binner.cpp:305-325).
+ * A record's supports[] slice is its taxon_support_ vector: upper node first, lower node last,
+ * depth[lower] - depth[upper] + 1 entries (predictionrecord.hh:152-158, 330-372). */
+typedef struct trpa_bin_record {
+  uint32_t lower_node, upper_node;
+  uint32_t support_begin;   /* first entry of this record in supports[] */
+  uint32_t query_length;    /* seqlen= */
+  uint32_t query_id;        /* dense id of the record's own sequence identifier (a group sums each length once) */
+  uint32_t reserved;
+} trpa_bin_record;
+typedef struct trpa_bin_params {
+  float signal_majority;              /* -j (default 0.7) */
+  uint32_t min_support_per_sequence;  /* -s (default 50) */
+  uint32_t min_support_in_sample;     /* -m as a position count (>= 1), or 0 */
+  float min_support_in_sample_fraction; /* -m as a fraction of the root's support (value containing '.'), or 0 */
+  uint32_t n_ranks;                   /* identity constraints: pid_per_rank[rank_of_node[n]] (< 0: none); 0 = no -i given */
+  uint32_t reserved;
+} trpa_bin_params;
+#define TRPA_BIN_EMPTY 0      /* every record of the group was removed by the noise filter: no output line */
+#define TRPA_BIN_SINGLE 1     /* one record: passed through (binner.cpp:301-303) */
+#define TRPA_BIN_DIRECT 2
+#define TRPA_BIN_FALLBACK 3
+typedef struct trpa_bin_result {
+  uint32_t node;            /* the taxon written to the binning file */
+  uint32_t support;         /* _TaxatorTK_Support column */
+  uint32_t length;          /* _TaxatorTK_Length column */
+  uint32_t mode;            /* TRPA_BIN_* */
+  uint32_t lower_node, upper_node;   /* the combined record's range (before the identity constraints) */
+  uint32_t lower_support, upper_support;
+} trpa_bin_result;
+typedef struct trpa_bin_stats {
+  uint64_t nested_taxa;     /* taxa with sample support ("N nested taxa", binner.cpp:253) */
+  uint64_t root_support;    /* total support of the root */
+  uint64_t pruned_taxa;     /* "N taxa removed" (binner.cpp:282) */
+  uint64_t min_support_found;
+} trpa_bin_stats;
+/* group_begin has n_groups + 1 entries: group g owns records[group_begin[g] .. group_begin[g+1]) in input order.
+ * rank_of_node / pid_per_rank are only read when params->n_ranks > 0 (nullable otherwise).  Uses the taxonomy
+ * loaded with trpa_load_taxonomy. */
+int trpa_bin_batch(trpa_ctx* ctx, const trpa_bin_params* params, const trpa_bin_record* records, uint32_t n_records,
+                   const uint32_t* supports, uint32_t n_supports, const uint32_t* group_begin, uint32_t n_groups,
+                   const uint8_t* rank_of_node, const float* pid_per_rank, trpa_bin_result* out, trpa_bin_stats* stats);
 
 /* ---- lower-level entry points (unit tests, micro-benchmarks) ------------------------------ */
 /* edit distance of n_pairs pairs over a private ASCII sequence table; == getAlignmentDNA distance

@@ -14,6 +14,7 @@
 #include <deque>
 #include <functional>
 #include <iostream>
+#include <list>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -146,6 +147,7 @@ class scoped_ptr {
 template <class T>
 class ptr_vector {
  public:
+  typedef size_t size_type;
   ptr_vector() {}
   explicit ptr_vector(size_t reserve) { v_.reserve(reserve); }
   ~ptr_vector() { for (T* p : v_) delete p; }
@@ -156,6 +158,52 @@ class ptr_vector {
   size_t size() const { return v_.size(); }
  private:
   std::vector<T*> v_;
+};
+
+// owning list of heap objects (binner.cpp): iterators dereference to T&, a copy clones every element
+template <class T>
+class ptr_list {
+  typedef std::list<T*> L;
+ public:
+  template <class It, class Ref, class Ptr>
+  class iter {
+   public:
+    typedef std::bidirectional_iterator_tag iterator_category;
+    typedef T value_type; typedef std::ptrdiff_t difference_type; typedef Ptr pointer; typedef Ref reference;
+    iter() {}
+    iter(It i) : i_(i) {}
+    template <class It2, class R2, class P2> iter(const iter<It2, R2, P2>& o) : i_(o.base()) {}
+    Ref operator*() const { return **i_; }
+    Ptr operator->() const { return *i_; }
+    iter& operator++() { ++i_; return *this; }
+    iter operator++(int) { iter t(*this); ++i_; return t; }
+    iter& operator--() { --i_; return *this; }
+    bool operator==(const iter& o) const { return i_ == o.i_; }
+    bool operator!=(const iter& o) const { return i_ != o.i_; }
+    It base() const { return i_; }
+   private:
+    It i_;
+  };
+  typedef iter<typename L::iterator, T&, T*> iterator;
+  typedef iter<typename L::const_iterator, const T&, const T*> const_iterator;
+  typedef size_t size_type;
+  ptr_list() {}
+  ptr_list(const ptr_list& o) { for (T* p : o.l_) l_.push_back(new T(*p)); }
+  ptr_list& operator=(const ptr_list&) = delete;
+  ~ptr_list() { for (T* p : l_) delete p; }
+  void push_back(T* p) { l_.push_back(p); }
+  iterator begin() { return iterator(l_.begin()); }
+  iterator end() { return iterator(l_.end()); }
+  const_iterator begin() const { return const_iterator(l_.begin()); }
+  const_iterator end() const { return const_iterator(l_.end()); }
+  iterator erase(iterator it) { delete *it.base(); return iterator(l_.erase(it.base())); }
+  bool empty() const { return l_.empty(); }
+  size_type size() const { return l_.size(); }
+  T& front() { return *l_.front(); }
+  const T& front() const { return *l_.front(); }
+  T& back() { return *l_.back(); }
+ private:
+  L l_;
 };
 
 template <class T>
@@ -179,7 +227,15 @@ inline bool exists(const std::string& p) { struct stat st; return ::stat(p.c_str
 }
 
 // ------------------------------------------------------------------------------------- regex
-typedef std::regex regex;
+class regex : public std::regex {   // + size() of the expression text (binner.cpp:47)
+ public:
+  regex() {}
+  regex(const std::string& s) : std::regex(s), n_(s.size()) {}
+  regex(const char* s) : std::regex(s), n_(std::string(s).size()) {}
+  size_t size() const { return n_; }
+ private:
+  size_t n_ = 0;
+};
 typedef std::cmatch cmatch;
 typedef std::regex_error regex_error;
 using std::regex_match;
@@ -394,10 +450,16 @@ inline std::ostream& operator<<(std::ostream& os, const options_description& o) 
 }
 
 struct parsed_options { const options_description* desc; std::vector<std::pair<std::string, std::vector<std::string>>> items; };
+struct variable_value {   // vm["key"].as< const std::vector<std::string> >(): the raw tokens of the option
+  std::vector<std::string> toks;
+  template <class T> const std::vector<std::string>& as() const { return toks; }
+};
 class variables_map {
  public:
   size_t count(const std::string& k) const { return seen_.count(k) ? 1 : 0; }
+  const variable_value& operator[](const std::string& k) const { return raw_.at(k); }
   std::map<std::string, int> seen_;
+  std::map<std::string, variable_value> raw_;
 };
 class command_line_parser {
  public:
@@ -435,7 +497,11 @@ class command_line_parser {
 inline void store(const parsed_options& po, variables_map& vm) {
   for (const auto& d : po.desc->opts_) if (d.sem) { d.sem->apply_default(); if (d.sem->has_default()) vm.seen_[d.lng] = 1; }
   for (const auto& it : po.items) {
-    for (const auto& d : po.desc->opts_) if (d.lng == it.first) { if (d.sem) d.sem->parse(it.second); vm.seen_[d.lng] = 1; }
+    for (const auto& d : po.desc->opts_) if (d.lng == it.first) {
+      if (d.sem) d.sem->parse(it.second);
+      vm.seen_[d.lng] = 1;
+      for (const auto& t : it.second) vm.raw_[d.lng].toks.push_back(t);
+    }
   }
 }
 inline void notify(variables_map&) {}

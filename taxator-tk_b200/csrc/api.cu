@@ -67,6 +67,12 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// a DevBuf local to one call: released on every return path
+template <class T>
+struct ScopedBuf : DevBuf<T> {
+  ~ScopedBuf() { this->release(); }
+};
+
 struct Store {
   int alphabet = -1;
   u32 n_seq = 0;
@@ -129,7 +135,7 @@ struct trpa_ctx {
   // taxonomy
   DevBuf<u32> t_parent, t_left, t_right;
   DevBuf<uint8_t> t_depth;
-  u32 n_nodes = 0, root = 0;
+  u32 n_nodes = 0, root = 0, max_depth = 0;
   Store store[2];
   // batch (whole batch resident)
   std::vector<u32> chunk_begin;  // segment index boundaries
@@ -533,6 +539,8 @@ int trpa_load_taxonomy(trpa_ctx* c, const uint32_t* parent, const uint32_t* left
   CK(cudaMemcpyAsync(c->t_depth.p, depth, 1ull * n_nodes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->n_nodes = n_nodes; c->root = root;
+  c->max_depth = 0;
+  for (u32 i = 0; i < n_nodes; ++i) c->max_depth = std::max<u32>(c->max_depth, depth[i]);
   return 0;
 }
 
@@ -1263,6 +1271,69 @@ int trpa_predict_lca_batch(trpa_ctx* c, const trpa_lca_params* pp, const trpa_se
   if (kernel_ms) *kernel_ms = ms / repeat;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   c->prof.launches_other += (u64)repeat;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ binner
+int trpa_bin_batch(trpa_ctx* c, const trpa_bin_params* pp, const trpa_bin_record* records, uint32_t n_records,
+                   const uint32_t* supports, uint32_t n_supports, const uint32_t* group_begin, uint32_t n_groups,
+                   const uint8_t* rank_of_node, const float* pid_per_rank, trpa_bin_result* out, trpa_bin_stats* stats) {
+  if (!c || !pp || (n_records && (!records || !supports)) || !group_begin || (n_groups && !out)) { set_error("bad arguments"); return TRPA_ERR_ARG; }
+  if (c->n_nodes == 0) { set_error("taxonomy not loaded"); return TRPA_ERR_STATE; }
+  if (pp->n_ranks && (!rank_of_node || !pid_per_rank)) { set_error("identity constraints need rank_of_node and pid_per_rank"); return TRPA_ERR_ARG; }
+  if (use_device(c)) return TRPA_ERR_CUDA;
+  // validation: groups contiguous and in order; ranges are ancestor paths; supports slices inside the table
+  if (group_begin[0] != 0 || group_begin[n_groups] != n_records) { set_error("group table must cover the record table"); return TRPA_ERR_ARG; }
+  for (u32 g = 0; g < n_groups; ++g) if (group_begin[g] > group_begin[g + 1]) { set_error("group table not ascending"); return TRPA_ERR_ARG; }
+  if (n_records) {
+    std::vector<uint8_t> h_depth(c->n_nodes);
+    std::vector<u32> h_parent(c->n_nodes);
+    CK(cudaMemcpyAsync(h_depth.data(), c->t_depth.p, c->n_nodes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_parent.data(), c->t_parent.p, 4ull * c->n_nodes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (u32 r = 0; r < n_records; ++r) {
+      const trpa_bin_record& b = records[r];
+      if (b.lower_node >= c->n_nodes || b.upper_node >= c->n_nodes || h_depth[b.lower_node] < h_depth[b.upper_node]) { set_error("prediction record: bad node range"); return TRPA_ERR_ARG; }
+      u32 x = b.lower_node;
+      while (h_depth[x] > h_depth[b.upper_node]) x = h_parent[x];
+      if (x != b.upper_node) { set_error("prediction record: upper node is not an ancestor of the lower node"); return TRPA_ERR_ARG; }
+      if ((u64)b.support_begin + (h_depth[b.lower_node] - h_depth[b.upper_node] + 1u) > n_supports) { set_error("prediction record: support slice out of range"); return TRPA_ERR_ARG; }
+    }
+  }
+  const u32 D1 = c->max_depth + 1;
+  ScopedBuf<trpa_bin_record> d_rec; ScopedBuf<u32> d_sup, d_gb, d_nodes3, d_lower, d_cur, d_majn, d_pathn, d_stats;
+  ScopedBuf<float> d_majs, d_pid; ScopedBuf<uint8_t> d_alive, d_state, d_pathb, d_rank; ScopedBuf<unsigned short> d_tot, d_pathd, d_patht;
+  ScopedBuf<trpa_bin_result> d_out;
+  if (d_rec.ensure(n_records + 1) || d_sup.ensure(n_supports + 1) || d_gb.ensure(n_groups + 1) || d_nodes3.ensure(3ull * c->n_nodes) ||
+      d_lower.ensure(n_records + 1) || d_cur.ensure(n_records + 1) || d_majn.ensure(n_records + 1) || d_majs.ensure(n_records + 1) ||
+      d_alive.ensure(n_records + 1) || d_state.ensure(n_records + 1) || d_tot.ensure((size_t)(n_records + 1) * D1) ||
+      d_pathn.ensure((size_t)(n_groups + 1) * D1) || d_pathd.ensure((size_t)(n_groups + 1) * D1) || d_patht.ensure((size_t)(n_groups + 1) * D1) ||
+      d_pathb.ensure((size_t)(n_groups + 1) * D1) || d_out.ensure(n_groups + 1) || d_stats.ensure(4) ||
+      (pp->n_ranks && (d_rank.ensure(c->n_nodes) || d_pid.ensure(pp->n_ranks))))
+    return TRPA_ERR_NOMEM;
+  struct SyncGuard { cudaStream_t st; ~SyncGuard() { cudaStreamSynchronize(st); } } sync_guard{c->stream};
+  if (n_records) CK(cudaMemcpyAsync(d_rec.p, records, sizeof(trpa_bin_record) * n_records, cudaMemcpyHostToDevice, c->stream));
+  if (n_supports) CK(cudaMemcpyAsync(d_sup.p, supports, 4ull * n_supports, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_gb.p, group_begin, 4ull * (n_groups + 1), cudaMemcpyHostToDevice, c->stream));
+  if (pp->n_ranks) {
+    for (u32 i = 0; i < c->n_nodes; ++i) if (rank_of_node[i] >= pp->n_ranks) { set_error("rank_of_node out of range"); return TRPA_ERR_ARG; }
+    CK(cudaMemcpyAsync(d_rank.p, rank_of_node, c->n_nodes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_pid.p, pid_per_rank, sizeof(float) * pp->n_ranks, cudaMemcpyHostToDevice, c->stream));
+  }
+  BinScratch S;
+  S.node_support = d_nodes3.p; S.node_seen = d_nodes3.p + c->n_nodes; S.node_pruned = d_nodes3.p + 2ull * c->n_nodes;
+  S.lower = d_lower.p; S.alive = d_alive.p; S.state = d_state.p; S.curnode = d_cur.p; S.maj_node = d_majn.p; S.maj_sum = d_majs.p;
+  S.tot = d_tot.p; S.path_node = d_pathn.p; S.path_direct = d_pathd.p; S.path_total = d_patht.p; S.path_branch = d_pathb.p;
+  CK(launch_binner(d_rec.p, n_records, d_sup.p, d_gb.p, n_groups, dev_tax(c), c->n_nodes, c->max_depth, *pp,
+                   pp->n_ranks ? d_rank.p : nullptr, pp->n_ranks ? d_pid.p : nullptr, S, d_out.p, d_stats.p, c->stream));
+  c->prof.launches_other += 4;
+  u32 h_stats[4] = {0, 0, 0, 0};
+  u32 h_root = 0;
+  if (n_groups) CK(cudaMemcpyAsync(out, d_out.p, sizeof(trpa_bin_result) * n_groups, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(h_stats, d_stats.p, sizeof(h_stats), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&h_root, S.node_support + c->root, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (stats) { stats->nested_taxa = h_stats[0]; stats->pruned_taxa = h_stats[1]; stats->min_support_found = h_stats[2]; stats->root_support = h_root; }
   return 0;
 }
 

@@ -23,6 +23,18 @@ cudaError_t launch_lca_models(const trpa_segment* segs, u32 n_segs, const trpa_c
                               const uint8_t* uncl, const Taxonomy& tax, const trpa_lca_params& pp, trpa_result* out,
                               cudaStream_t stream);
 
+// consensus binning (binner.cu): scratch of one trpa_bin_batch call, all device pointers
+struct BinScratch {
+  u32* node_support; u32* node_seen; u32* node_pruned;       // n_nodes each
+  u32* lower; uint8_t* alive; uint8_t* state; u32* curnode;  // n_records each
+  u32* maj_node; float* maj_sum;                             // n_records each
+  unsigned short* tot;                                       // n_records x (max_depth + 1)
+  u32* path_node; unsigned short* path_direct; unsigned short* path_total; uint8_t* path_branch;   // n_groups x (max_depth + 1)
+};
+cudaError_t launch_binner(const trpa_bin_record* recs, u32 n_records, const u32* supports, const u32* group_begin, u32 n_groups,
+                          const Taxonomy& tax, u32 n_nodes, u32 max_depth, const trpa_bin_params& pp, const uint8_t* rank_of_node,
+                          const float* pid_per_rank, BinScratch& S, trpa_bin_result* out, u32* stats4, cudaStream_t stream);
+
 // BLOSUM62 linear-gap NW with traced length; out2[pair.out] = {mutual, #diagonal steps}
 // scratch: scratch_stride int2 per pair, needed only when a pair's A is longer than 512 residues
 cudaError_t launch_protein(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,

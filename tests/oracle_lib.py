@@ -31,7 +31,8 @@ def _newer(target, *sources):
 def build_oracle():
     so = os.path.join(ORACLE_DIR, "librpa_oracle.so")
     src = os.path.join(ORACLE_DIR, "rpa_oracle.cpp")
-    if not _newer(so, src, os.path.join(ORACLE_DIR, "blosum62_table.h")):
+    if not _newer(so, src, os.path.join(ORACLE_DIR, "blosum62_table.h"), os.path.join(ORACLE_DIR, "binner_oracle.cpp"),
+                  os.path.join(ROOT, "include", "taxator_rpa_b200.h")):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "librpa_oracle.so"], stdout=subprocess.DEVNULL)
     return so
 

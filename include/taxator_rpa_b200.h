@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TRPA_ABI_VERSION 7
+#define TRPA_ABI_VERSION 8
 
 #define TRPA_OK 0
 #define TRPA_ERR_CUDA (-1)
@@ -90,6 +90,20 @@ typedef struct trpa_result {
   uint32_t kind;
   uint64_t cells;                     /* sum |A|*|B| over those alignments (GCUPS numerator) */
 } trpa_result;
+
+/* One consumed pairwise alignment of a segment, in the order the reference would compute them (what the verbose
+ * per-alignment log of `taxator -l` is written from, hh:516-837).  a / b: record index inside the segment's record
+ * set in SortFilter order (the `i` of the reference's log), TRPA_TRACE_QUERY for the query range.  r0 / r1: the raw
+ * integers of the alignment -- nucleotide: r0 = edit distance; protein: r0 = mutual BLOSUM62 score, r1 = number of
+ * diagonal steps of the traced path, self = sum of the two self scores (hh:190-191). */
+#define TRPA_TRACE_QUERY 0xffffffffu
+typedef struct trpa_trace_entry {
+  uint32_t seg;
+  uint32_t a, b;
+  int32_t r0, r1;
+  uint32_t len_a, len_b;
+  uint32_t self;
+} trpa_trace_entry;
 
 /* Per-kernel device time accumulated since the last reset (CUDA events on the context's stream). */
 typedef struct trpa_profile {
@@ -164,6 +178,12 @@ int trpa_batch_upload(trpa_ctx* ctx, const trpa_segment* segs, uint32_t n_segs, 
                       uint32_t n_cands);
 int trpa_batch_run(trpa_ctx* ctx);
 int trpa_batch_download(trpa_ctx* ctx, trpa_result* out);
+/* Alignment trace (verbose log, `taxator -l`): trpa_set_trace(ctx, 1) makes the following batches record every
+ * consumed alignment; trpa_batch_trace copies the entries of the last trpa_batch_run to `out` (capacity `cap`
+ * entries, *n = entries available; call with cap = 0 to size the buffer), ordered by segment and, inside a segment,
+ * in the reference's order.  Results never depend on tracing. */
+int trpa_set_trace(trpa_ctx* ctx, int on);
+int trpa_batch_trace(trpa_ctx* ctx, trpa_trace_entry* out, uint64_t cap, uint64_t* n);
 
 /* Multi-GPU (taxator.cpp:181-210 parallelises over record sets only): segments are independent, so a batch is cut
  * into `world` contiguous shards, one per GPU / context, and the fixed-size result records are concatenated in

@@ -165,6 +165,11 @@ struct trpa_ctx {
   DevBuf<u32> arena_n;
   DevBuf<uint8_t> arena_aa;
   u64 arena_units = 0;
+  // alignment trace (verbose log): on/off, device buffer, entries recorded by the last run
+  int trace_on = 0;
+  DevBuf<trpa_trace_entry> d_trace;
+  u64 trace_used = 0;
+  bool trace_overflow = false;
   int band = 1;               // 1: Ukkonen band (exact), 0: full DP matrix
   int wedge = 1;              // 1: let the band narrow along the matrix where a certificate can prove it (exact)
   // pipes: independent sub-batch pipelines whose rounds overlap on the GPU (pipe[0] runs on `stream`)
@@ -472,7 +477,7 @@ void trpa_destroy(trpa_ctx* c) {
   c->d_segs.release(); c->d_cands.release(); c->d_cands_raw.release(); c->d_results.release(); c->d_state.release();
   c->d_qd.release(); c->d_qsim.release(); c->d_bf_d.release(); c->d_cflags.release(); c->d_og_i.release(); c->d_tag.release();
   c->d_bf_node.release(); c->d_og_d.release(); c->d_res.release(); c->d_descs.release(); c->d_pairs.release();
-  c->d_pairs_sorted.release(); c->d_stage.release();
+  c->d_pairs_sorted.release(); c->d_stage.release(); c->d_trace.release();
   c->arena_planes.release(); c->arena_codes.release(); c->arena_n.release();
   c->l_segs.release(); c->l_cands.release(); c->l_ev.release(); c->l_un.release(); c->l_out.release(); c->arena_aa.release();
   for (int i = trpa_ctx::kMaxPipes - 1; i >= 0; --i) c->pipe[i].release();
@@ -857,6 +862,10 @@ static int start_chunk(trpa_ctx* c, Pipe& P, int pipe_index, size_t& next_chunk,
   P.B.arena_base = (u32)(c->arena_units * (u64)pipe_index);
   P.B.arena_capacity = (u32)c->arena_units;
   P.B.spec_k = 0;
+  if (c->trace_on && c->d_trace.p) {   // the chunk appends behind what earlier chunks of this run recorded
+    P.B.trace = c->d_trace.p + c->trace_used;
+    P.B.trace_capacity = (u32)std::min<u64>(0xffffffffull, c->d_trace.cap - c->trace_used);
+  }
   P.pairs = P.B.pairs;
   P.sorted = c->d_pairs_sorted.p + c->chunk_qoff[ch];
   CK(cudaMemsetAsync(P.d_counters.p, 0, sizeof(u32) * kNumCounters, P.stream));
@@ -890,6 +899,11 @@ static int step_pipe(trpa_ctx* c, Pipe& P, int pipe_index, size_t& next_chunk, c
       const u64 units = P.h_counters[CN_ARENA];
       c->prof.bytes_stage += protein ? (units * 13) / 8 : units * 32;
       if (!protein) { const int rc = harvest_band_stats(c, P); if (rc) return rc; }
+      if (P.B.trace) {
+        const u64 got = P.h_counters[CN_TRACE];
+        if (got > P.B.trace_capacity) c->trace_overflow = true;
+        c->trace_used += std::min<u64>(got, P.B.trace_capacity);
+      }
       return start_chunk(c, P, pipe_index, next_chunk, base);
     }
     P.n_pairs = n_pairs;
@@ -969,11 +983,18 @@ int trpa_batch_run(trpa_ctx* c) {
   B.res_nt = c->d_res.p; B.res_aa = c->d_res.p;
   B.descs = c->d_descs.p; B.arena_capacity = (u32)c->arena_units; B.arena_base = 0;
   B.pairs = c->d_pairs.p; B.stage = c->d_stage.p; B.counters = nullptr; B.results = c->d_results.p;
+  B.trace = nullptr; B.trace_capacity = 0;
+  c->trace_used = 0; c->trace_overflow = false;
+  if (c->trace_on) {
+    // every record can be realigned against the query and against each anchor; 8 entries per record + 64 per
+    // segment covers the inputs the log is used on (an overflow is reported, never silent)
+    if (c->d_trace.ensure((size_t)n_cands * 8 + (size_t)n_segs * 64 + 1024)) return TRPA_ERR_NOMEM;
+  }
   if (protein) CK(ensure_blosum_constant(c->device));
 
   // the chunks of the batch are worked on by run_pipes pipes at the same time; the host advances
   // them round-robin, so while it waits for one pipe the others have work queued on the GPU
-  const int K = c->run_pipes;
+  const int K = c->trace_on ? 1 : c->run_pipes;   // the trace is appended chunk after chunk
   for (int k = 0; k < K; ++k) { const int rc = c->pipe[k].init(nullptr); if (rc) return rc; }
   if (K > 1) {   // the other pipes start after whatever is queued on the context's stream
     Pipe& P0 = c->pipe[0];
@@ -1012,6 +1033,27 @@ int trpa_batch_download(trpa_ctx* c, trpa_result* out) {
   if (use_device(c)) return TRPA_ERR_CUDA;
   CK(cudaMemcpyAsync(out, c->d_results.p, sizeof(trpa_result) * c->n_segs, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int trpa_set_trace(trpa_ctx* c, int on) {
+  if (!c) { set_error("null ctx"); return TRPA_ERR_ARG; }
+  c->trace_on = on ? 1 : 0;
+  return 0;
+}
+
+int trpa_batch_trace(trpa_ctx* c, trpa_trace_entry* out, uint64_t cap, uint64_t* n) {
+  if (!c || !n || (cap && !out)) { set_error("bad arguments"); return TRPA_ERR_ARG; }
+  if (!c->batch_ready) { set_error("no batch uploaded"); return TRPA_ERR_STATE; }
+  if (c->trace_overflow) { set_error("alignment trace overflow: run the log on smaller batches"); return TRPA_ERR_NOMEM; }
+  *n = c->trace_used;
+  if (cap == 0 || c->trace_used == 0) return 0;
+  if (cap < c->trace_used) { set_error("trace buffer too small"); return TRPA_ERR_ARG; }
+  if (use_device(c)) return TRPA_ERR_CUDA;
+  CK(cudaMemcpyAsync(out, c->d_trace.p, sizeof(trpa_trace_entry) * c->trace_used, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  // device threads append concurrently: order by segment, keeping each segment's own (program) order
+  std::stable_sort(out, out + c->trace_used, [](const trpa_trace_entry& x, const trpa_trace_entry& y) { return x.seg < y.seg; });
   return 0;
 }
 

@@ -72,7 +72,7 @@ struct Taxonomy {
 };
 
 // Work queues of one round (device memory); counters[] is what the host reads back.
-enum Counter : uint32_t { CN_PAIRS = 0, CN_STAGE, CN_ACTIVE, CN_ARENA, CN_OVERFLOW, CN_END };
+enum Counter : uint32_t { CN_PAIRS = 0, CN_STAGE, CN_ACTIVE, CN_ARENA, CN_OVERFLOW, CN_TRACE, CN_END };
 constexpr uint32_t kNumCounters = 8;
 
 struct Batch {
@@ -109,6 +109,9 @@ struct Batch {
   StageReq* stage;
   uint32_t* counters;
   trpa_result* results;
+  // optional alignment trace (verbose log): entries appended at counters[CN_TRACE], nullptr = off
+  trpa_trace_entry* trace;
+  uint32_t trace_capacity;
 };
 
 TRPA_HD uint32_t tx_lca(const Taxonomy& t, uint32_t A, uint32_t B) {
@@ -236,6 +239,20 @@ struct Machine {
   // distance/similarity of a finished alignment (hh:133-171 / hh:173-242)
   TRPA_HD void read_alignment(uint32_t slot, uint32_t da, uint32_t db, float& dist, float& sim) const {
     const uint32_t la = B.descs[da].len, lb = B.descs[db].len;
+    if (B.trace) {   // every call is one alignment the reference computes at this point of its control flow
+      const uint32_t k = TRPA_ATOMIC_ADD_U32(&B.counters[CN_TRACE], 1u);
+      if (k < B.trace_capacity) {
+        trpa_trace_entry e;
+        e.seg = s;
+        e.a = da < B.n_segs ? TRPA_TRACE_QUERY : da - B.n_segs - S.cbeg;
+        e.b = db < B.n_segs ? TRPA_TRACE_QUERY : db - B.n_segs - S.cbeg;
+        e.r0 = B.protein ? B.res_aa[2 * slot] : B.res_nt[slot];
+        e.r1 = B.protein ? B.res_aa[2 * slot + 1] : 0;
+        e.len_a = la; e.len_b = lb;
+        e.self = B.protein ? B.descs[da].pad + B.descs[db].pad : 0u;
+        B.trace[k] = e;
+      }
+    }
     if (!B.protein) {
       const int d = B.res_nt[slot];
       const int llong = (int)(la > lb ? la : lb), lshort = (int)(la > lb ? lb : la);

@@ -17,6 +17,7 @@
 #include "rpa_model.h"
 #include "seqstore.h"
 #include "taxonomy.h"
+#include "verbose_log.h"
 
 using namespace taxator_b200;
 
@@ -52,7 +53,7 @@ static void usage(std::ostream& os) {
         "  -f [ --ref-sequences ] arg        reference sequences FASTA\n"
         "  -i [ --ref-sequences-index ] arg  reference FASTA index (.fai)\n"
         "  -p [ --processors ] arg (=1)      accepted for compatibility (the work runs on the GPUs)\n"
-        "  -l [ --logfile ] arg (=/dev/null) per-segment STATS log\n"
+        "  -l [ --logfile ] arg (=/dev/null) verbose per-alignment log (ID/PASS/+ALN/EXT/SCORE/RANGE/STATS lines)\n"
         "  -b [ --dataformat ] arg (=nucleotide)  nucleotide or protein\n"
         "  -r [ --ranks ] arg...             node ranks at which to do predictions\n"
         "  -s [ --split-alignments ] arg (=1)\n"
@@ -278,12 +279,35 @@ int main(int argc, char** argv) {
       io.split = opt.split_alignments;
       io.block_bytes = opt.batch_bytes;
       const bool want_log = opt.logfile != "/dev/null";
+      if (want_log) {
+        // -l: the reference's verbose per-alignment log (hh:341-838).  The first GPU places the block and records the
+        // alignments it consumed; the log is written from that trace, segment by segment in input order.
+        VerboseLogContext lc;
+        lc.tax = &tax; lc.q_store = &q_store; lc.db_store = &db_store; lc.protein = protein;
+        lc.exclude_factor = opt.filterout;
+        lc.reeval_bandwidth_factor = 1. - opt.toppercent;
+        std::vector<trpa_trace_entry> trace;
+        total_sets = run_prediction_fast_blocks(
+            stdin, mapping, tax, q_store, db_store, io,
+            [&](FlatBlock& b) {
+              model.predictFlatTraced(b.segs.data(), (uint32_t)b.segs.size(), b.cands.data(), (uint32_t)b.cands.size(), b.res.data(), trace);
+              size_t t = 0;
+              for (size_t i = 0; i < b.segs.size(); ++i) {
+                size_t e = t;
+                while (e < trace.size() && trace[e].seg == i) ++e;
+                write_segment_log(lc, std::string(b.meta[i].qid, b.meta[i].qid_len), b.segs[i].query_seq, b.cands.data() + b.segs[i].cand_begin,
+                                  b.segs[i].cand_count, b.res[i], trace.data() + t, e - t, logsink);
+                t = e;
+              }
+            },
+            std::cout, nullptr, &model.mutable_stats(), &stage_times);
+      } else
       total_sets = run_prediction_fast(
           stdin, mapping, tax, q_store, db_store, io,
           [&](const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands, uint32_t n_cands, trpa_result* res) {
             model.predictFlat(segs, n_segs, cands, n_cands, res);
           },
-          std::cout, want_log ? &logsink : nullptr, &model.mutable_stats(), &stage_times);
+          std::cout, nullptr, &model.mutable_stats(), &stage_times);
     }
     auto t2 = std::chrono::steady_clock::now();
     if (opt.timing) {

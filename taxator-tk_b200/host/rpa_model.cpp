@@ -169,6 +169,24 @@ void RPAPredictionModelGPU::predictFlat(const trpa_segment* segs, uint32_t n_seg
   for (const auto& e : errors) if (!e.empty()) throw TaxatorError("GPU prediction failed: " + e);
 }
 
+void RPAPredictionModelGPU::predictFlatTraced(const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands,
+                                              uint32_t n_cands, trpa_result* res, std::vector<trpa_trace_entry>& trace) {
+  trace.clear();
+  if (!n_segs) return;
+  trpa_ctx* c = ctx_[0];
+  uint64_t n = 0;
+  int rc = trpa_set_trace(c, 1);
+  if (!rc) rc = trpa_predict_batch(c, segs, n_segs, cands, n_cands, res);
+  if (!rc) rc = trpa_batch_trace(c, nullptr, 0, &n);
+  if (!rc && n) {
+    trace.resize(n);
+    rc = trpa_batch_trace(c, trace.data(), n, &n);
+  }
+  const std::string msg = rc ? trpa_last_error() : "";
+  trpa_set_trace(c, 0);
+  if (rc) throw TaxatorError("GPU prediction failed: " + msg);
+}
+
 void RPAPredictionModelGPU::predictBatch(std::vector<RecordSet>& recordsets, std::vector<PredictionRecord>& precs,
                                          std::ostream& logsink) {
   const size_t n = recordsets.size();

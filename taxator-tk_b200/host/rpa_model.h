@@ -96,6 +96,11 @@ class RPAPredictionModelGPU : public TaxonPredictionModel<RecordSet> {
   void predictFlat(const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands, uint32_t n_cands,
                    trpa_result* res);
 
+  // same on the first GPU only, recording every consumed alignment (trpa_set_trace / trpa_batch_trace): what the
+  // verbose log (-l) is written from; trace entries come back ordered by segment
+  void predictFlatTraced(const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands, uint32_t n_cands,
+                         trpa_result* res, std::vector<trpa_trace_entry>& trace);
+
   // a store as the first GPU packed it (what write_refpack() puts into a .trpk file); which = 0 query, 1 reference
   void exportStore(int which, std::vector<uint64_t>& woff, std::vector<uint32_t>& len, std::vector<char>& payload, int& alphabet);
 

@@ -24,7 +24,7 @@ extern "C" int hm_predict_batch(
     const uint8_t* r_codes, const uint64_t* r_off, const uint32_t* r_len, uint32_t r_n,
     int protein, float exclude_factor, float toppercent,
     const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands_in, uint32_t n_cands,
-    trpa_result* results, uint32_t* rounds_out, uint32_t spec_k) {
+    trpa_result* results, uint32_t* rounds_out, uint32_t spec_k, trpa_trace_entry* trace, uint32_t trace_cap, uint32_t* trace_n) {
   std::vector<trpa_candidate> cands(cands_in, cands_in + n_cands);
   sort_candidates(segs, n_segs, cands.data());
 
@@ -54,6 +54,7 @@ extern "C" int hm_predict_batch(
   B.res_nt = res_nt.data(); B.res_aa = res_aa.data();
   B.descs = descs.data(); B.arena_capacity = 0xffffffffu; B.arena_base = 0;
   B.pairs = pairs.data(); B.stage = stage.data(); B.counters = counters.data(); B.results = results;
+  B.trace = trace; B.trace_capacity = trace_cap;
 
   uint32_t rounds = 0;
   for (;;) {
@@ -101,6 +102,7 @@ extern "C" int hm_predict_batch(
     if (rounds > 1000000) return -2;
   }
   if (rounds_out) *rounds_out = rounds;
+  if (trace_n) *trace_n = counters[CN_TRACE];
   (void)n_nodes; (void)q_n; (void)r_n;
   return 0;
 }

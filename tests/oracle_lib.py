@@ -145,11 +145,15 @@ def oracle_predict(fd: FlatData, exclude_factor=0.5, toppercent=0.05, want_pairs
     return (res, logs) if want_pairs else res
 
 
-def host_machine_predict(fd: FlatData, exclude_factor=0.5, toppercent=0.05, spec_k=0):
+def host_machine_predict(fd: FlatData, exclude_factor=0.5, toppercent=0.05, spec_k=0, want_trace=False):
     H = host_machine()
     n = len(fd.segs)
     res = np.zeros(n, dtype=synth.RESULT_DTYPE)
     rounds = ctypes.c_uint32(0)
+    trace_dtype = np.dtype([("seg", "<u4"), ("a", "<u4"), ("b", "<u4"), ("r0", "<i4"), ("r1", "<i4"), ("len_a", "<u4"),
+                            ("len_b", "<u4"), ("self", "<u4")])
+    trace = np.zeros(len(fd.cands) * 8 + n * 64 + 16 if want_trace else 1, trace_dtype)
+    trace_n = ctypes.c_uint32(0)
     f = H.hm_predict_batch
     f.restype = ctypes.c_int
     rc = f(ptr(fd.parent, u32p), ptr(fd.left, u32p), ptr(fd.right, u32p), ptr(fd.depth, u8p),
@@ -159,8 +163,14 @@ def host_machine_predict(fd: FlatData, exclude_factor=0.5, toppercent=0.05, spec
            ctypes.c_int(int(fd.protein)), ctypes.c_float(exclude_factor), ctypes.c_float(toppercent),
            fd.segs.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(n),
            fd.cands.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(len(fd.cands)),
-           res.ctypes.data_as(ctypes.c_void_p), ctypes.byref(rounds), ctypes.c_uint32(spec_k))
+           res.ctypes.data_as(ctypes.c_void_p), ctypes.byref(rounds), ctypes.c_uint32(spec_k),
+           trace.ctypes.data_as(ctypes.c_void_p) if want_trace else None, ctypes.c_uint32(len(trace) if want_trace else 0),
+           ctypes.byref(trace_n))
     assert rc == 0, rc
+    if want_trace:
+        assert trace_n.value <= len(trace)
+        t = trace[:trace_n.value]
+        return res, rounds.value, t[np.argsort(t["seg"], kind="stable")]
     return res, rounds.value
 
 

@@ -1,0 +1,63 @@
+"""The verbose per-alignment log (core/src/taxonpredictionmodelsequence.hh:341-838, `taxator -l`).
+CPU: the product's log writer (host/verbose_log.cpp) fed with the alignment trace of the host-compiled state machine
+reproduces the log of the REAL reference (tests/golden/log_*.log.gz, generator make_golden_log.py) block for block --
+every ID / PASS / +ALN / current ... node / EXT / SCORE / NUMALN / RANGE / STATS line and, for protein, SeqAn's
+rendering of every alignment; only the three CPU-time columns of STATS are masked.
+GPU: the same through taxator-b200 -l (trace recorded by the decide kernel)."""
+import os
+import subprocess
+
+import pytest
+
+import log_util as lu
+import oracle_lib as ol
+
+
+@pytest.mark.parametrize("case", sorted(lu.LOG_CASES))
+@pytest.mark.parametrize("spec_k", [0, 1000])
+def test_log_writer_reproduces_reference_log(case, spec_k, tmp_path):
+    fd = ol.FlatData(lu.log_case_data(case))
+    res, _, trace = ol.host_machine_predict(fd, spec_k=spec_k, want_trace=True)
+    out = str(tmp_path / "ours.log")
+    lu.write_log(fd, res, trace, out)
+    ours = lu.blocks_of(open(out).read())
+    want = lu.golden_blocks(case)
+    assert len(ours) == len(want)
+    assert sorted(ours) == sorted(want)
+    if fd.protein:
+        assert any("        " in b and "|" in b for b in ours)    # alignment renderings present
+
+
+def test_log_writer_detects_a_wrong_trace(tmp_path):
+    fd = ol.FlatData(lu.log_case_data("nt_small"))
+    res, _, trace = ol.host_machine_predict(fd, want_trace=True)
+    bad = trace.copy()
+    bad["a"][len(bad) // 2] = 77          # not the pair the control flow asks for at this point
+    with pytest.raises(AssertionError, match="diverged"):
+        lu.write_log(fd, res, bad, str(tmp_path / "x.log"))
+    with pytest.raises(AssertionError, match="diverged"):
+        lu.write_log(fd, res, trace[:-1], str(tmp_path / "y.log"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(lu.LOG_CASES))
+def test_cli_verbose_log_matches_reference(case, tmp_path):
+    exe = os.path.join(ol.ROOT, "taxator-tk_b200", "bin", "taxator-b200")
+    data = lu.log_case_data(case)
+    d = str(tmp_path)
+    data.write_files(d)
+    env = dict(os.environ, TAXATORTK_TAXONOMY_NCBI=d)
+    cmd = [exe, "-a", "rpa", "-g", "mapping.tax", "-q", "query.fna", "-f", "ref.fna", "-i", "ref.fna.fai", "-l", "ours.log"]
+    if data.cfg.protein:
+        cmd += ["-b", "protein"]
+    outs = []
+    for extra in ([], ["--batch-bytes", "8192"]):     # one block / many blocks (the trace is per block)
+        if os.path.exists(os.path.join(d, "ours.log")):
+            os.remove(os.path.join(d, "ours.log"))
+        with open(os.path.join(d, "alignments.tsv"), "rb") as fin:
+            p = subprocess.run(cmd + extra, cwd=d, env=env, stdin=fin, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert p.returncode == 0, p.stderr.decode()
+        outs.append(p.stdout)
+        ours = lu.blocks_of(open(os.path.join(d, "ours.log")).read())
+        assert sorted(ours) == sorted(lu.golden_blocks(case))
+    assert outs[0] == outs[1]

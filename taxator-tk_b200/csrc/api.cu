@@ -516,6 +516,12 @@ int trpa_set_tuning(trpa_ctx* c, const char* key, int64_t value) {
   else if (k == "cost_step") c->plan.step = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
   else if (k == "cost_setup") c->plan.setup = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
   else if (k == "cost_setup_w") c->plan.setup_w = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 16));
+  else if (k == "wedge_max_k") c->plan.wedge_max_k = (u32)std::max<int64_t>(64, std::min<int64_t>(value, 1 << 22));
+  else if (k == "wedge_hint_s8") c->plan.wedge_hint_s8 = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 15));
+  else if (k == "wedge_hint_max_k") c->plan.wedge_hint_max_k = (u32)std::max<int64_t>(64, std::min<int64_t>(value, 1 << 22));
+  else if (k == "wedge_s8") c->plan.wedge_s8 = (u32)std::max<int64_t>(1, std::min<int64_t>(value, 15));
+  else if (k == "wedge_e0") c->plan.wedge_e0 = (u32)std::max<int64_t>(1, std::min<int64_t>(value, 1 << 16));
+  else if (k == "wedge_cushion") c->plan.wedge_cushion = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 16));
   else if (k == "plan_lanes") c->plan_lanes = value < 0 ? 0u : (u32)std::min<int64_t>(value, 1 << 30);
   else if (k == "wedge") c->wedge = value < 0 ? 0 : (value > 2 ? 2 : (int)value);   // 2: test hook, see plan_kernel
   else if (k == "la_cap") c->la_cap = (u32)std::max<int64_t>(1, value);

@@ -64,11 +64,12 @@ __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const Seq
       u32 ub = total + (n - m);                   // a valid alignment: d <= ub
       const u32 hint = pd.pad;
       bool from_hint = false;
+      u32 hint_value = 0;
       if (hint) {
         // an estimate gets a margin (the kernel verifies and widens); a true bound (kHintIsBound) is used as is
         const u32 hv = hint & ~kHintIsBound;
         const u32 hk = (hint & kHintIsBound) ? hv : (u32)min((uint64_t)hv * pp.hint_mul64 / 64u + pp.hint_add, (uint64_t)kPadKFull);
-        if (hk < ub) { ub = hk; from_hint = true; }
+        if (hk < ub) { ub = hk; from_hint = true; hint_value = hv; }
       }
       if (band > 1) ub = (u32)band;               // test hook: forced initial threshold
       k0 = ub < kPadKFull ? ub : kPadKFull - 1u;
@@ -76,13 +77,19 @@ __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const Seq
       // estimate of how fast errors accumulate along the alignment; 3/4 of it narrows the band
       // (measured, scripts/wedge_probe.py: pays from ~8 % divergence and 2 kb on; with half widths beyond
       // ~1000 the cheapest paths to far-off cells dodge most mismatches and the certificate fails)
-      const bool pays = m >= 2048u && total * 3u < m && total * 12u >= m && total + (n - m) <= 2048u;
-      if (wedge && !from_hint && band == 1 && (wedge == 2 ? m >= 256u : pays)) {
+      const bool pays = m >= 2048u && total * 3u < m && total * 12u >= m && total + (n - m) <= pp.wedge_max_k;
+      // threshold from an estimate (noisy long reads: the mismatch profile of an ungapped overlay says nothing once
+      // indels shift the diagonal): assume the estimated errors accumulate uniformly along the pattern
+      const bool pays_hint = from_hint && pp.wedge_hint_s8 && m >= 2048u && (uint64_t)hint_value * 3u < m &&
+                             (uint64_t)hint_value * 16u >= m && ub <= pp.wedge_hint_max_k;
+      if (wedge && band == 1 && (wedge == 2 ? (m >= 256u && !from_hint) : (from_hint ? pays_hint : pays))) {
         const u32 pos = min(m, (lane + 1u) * per * 32u);      // pattern rows covered up to this lane
         // rate in mismatches per 2^16 rows, rounded down
         u32 rate = pos * 8u >= m ? (u32)(((uint64_t)cum << 16) / pos) : 0xffffffffu;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) rate = min(rate, __shfl_xor_sync(0xffffffffu, rate, o));
+        const u32 s8 = from_hint ? pp.wedge_hint_s8 : pp.wedge_s8;
+        if (from_hint) rate = (u32)(((uint64_t)hint_value << 16) / m);
         // A cell at diagonal offset a of row `row` has seen the errors of its first (row - a) columns
         // only, and the count fluctuates: keep the full width until about 30 errors are expected
         // (x0 rows after the first a0), then  2 a + s rate (row - a - x0) = k - delta  with s = 3/4
@@ -90,13 +97,13 @@ __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const Seq
         // (the exit cells of the first strips have seen almost no errors yet: their certificate term is
         // about k0 itself, so k0 gets a small cushion over the distance bound)
         const u32 delta = n - m;
-        const u32 k0w = k0 + 16u;
+        const u32 k0w = k0 + pp.wedge_cushion;
         const u32 a0 = k0w > delta ? (k0w - delta) >> 1 : 0u;
         const uint64_t K = k0w > delta ? k0w - delta : 0u;
-        uint64_t x0l = rate ? ((30ull << 16) + rate - 1u) / rate : (uint64_t)m;
+        uint64_t x0l = rate ? (((uint64_t)pp.wedge_e0 << 16) + rate - 1u) / rate : (uint64_t)m;
         if (x0l > m) x0l = m;
         const u32 x0 = (u32)x0l;
-        const uint64_t sr = ((uint64_t)rate * 3u) >> 2;                  // s * rate, per 2^16 rows
+        const uint64_t sr = ((uint64_t)rate * s8) >> 3;                   // s * rate, per 2^16 rows (s = 3/4 by default)
         const uint64_t e_end = m > x0 ? (sr * (m - x0)) >> 16 : 0u;
         a1 = K > e_end ? (u32)(((K - e_end) << 16) / ((2ull << 16) - sr)) : 0u;
         if (a1 < 32u) a1 = 32u;

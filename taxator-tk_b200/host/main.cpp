@@ -172,9 +172,15 @@ int main(int argc, char** argv) {
       trpa_lca_params params;
       if (opt.algorithm == "dummy") params = LCAPredictionModelGPU::dummy();
       else if (opt.algorithm == "simple-lca") params = LCAPredictionModelGPU::simple();
-      else if (opt.algorithm == "megan-lca" || opt.algorithm == "ic-megan-lca")
+      else if (opt.algorithm == "megan-lca" || opt.algorithm == "ic-megan-lca") {
+        if (opt.minsupport >= 2)
+          // the filter counts rises of the running maximum in record-set order, and the reference orders records of
+          // equal (qstart, qstop) by heap address (alignmentrecord.hh:479): its own -c >= 2 output is allocator
+          // dependent.  This build uses the order of the input file, which is one of the orders the reference can take.
+          std::cerr << "taxator-b200: note: with -c >= 2 the reference's result depends on its allocator for records with "
+                       "equal query ranges; using input-file order" << std::endl;
         params = LCAPredictionModelGPU::megan(opt.ignore_unclassified, opt.toppercent, opt.minscore, (int)opt.minsupport, opt.maxevalue);
-      else if (opt.algorithm == "n-best-lca") params = LCAPredictionModelGPU::nbest((int)opt.nbest);
+      } else if (opt.algorithm == "n-best-lca") params = LCAPredictionModelGPU::nbest((int)opt.nbest);
       else {
         std::cout << "classification algorithm can either be: rpa (default), simple-lca, megan-lca, ic-megan-lca, n-best-lca" << std::endl;
         return EXIT_FAILURE;

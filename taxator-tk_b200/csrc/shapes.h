@@ -169,8 +169,10 @@ struct PlanParams {
   uint32_t tail_log2 = 22;   // latency penalty time + time^2 / 2^tail_log2 (>= 9)
   uint32_t word10 = 100, col10 = 35, step = 200, setup = 250, setup_w = 25;   // SASS + ncu region counts, profiles/r03_myers3_ncu.md
   // wedge (plan_kernel): the band narrows at wedge_s8 / 8 of the slowest prefix mismatch rate once wedge_e0 errors
-  // are expected; k0 gets wedge_cushion extra.  More aggressive = fewer cells, more failed certificates (re-runs).
-  uint32_t wedge_s8 = 6, wedge_e0 = 30, wedge_cushion = 16, wedge_max_k = 2048;
+  // are expected; k0 gets wedge_cushion extra.  More aggressive = fewer cells, more failed certificates (re-runs):
+  // measured on C2, s = 6/8: 283.7 k seg/s, 3 re-runs per step; 8/8: 296.2 k, 1074 re-runs (gpurun_out r2_07); C4 neutral.
+  // wedge_max_k: beyond ~2048 the certificates fail too often (C4 with 4096: 40 k re-runs per step, -13 %).
+  uint32_t wedge_s8 = 8, wedge_e0 = 30, wedge_cushion = 16, wedge_max_k = 2048;
   // the same for pairs whose threshold comes from a distance ESTIMATE (hint) instead of the mismatch profile: errors are
   // assumed to accumulate uniformly at hint / m; 0 = no wedge for such pairs
   uint32_t wedge_hint_s8 = 0, wedge_hint_max_k = 16384;

@@ -1072,11 +1072,21 @@ int trpa_batch_results_dev(trpa_ctx* c, void** dev_ptr, uint32_t* n_segs) {
 
 int trpa_predict_batch(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, const trpa_candidate* cands,
                        uint32_t n_cands, trpa_result* out) {
+  static const bool timing = getenv("TRPA_DEBUG_TIMING") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
   int rc = trpa_batch_upload(c, segs, n_segs, cands, n_cands);
   if (rc) return rc;
+  const auto t1 = std::chrono::steady_clock::now();
   rc = trpa_batch_run(c);
   if (rc) return rc;
-  return trpa_batch_download(c, out);
+  const auto t2 = std::chrono::steady_clock::now();
+  rc = trpa_batch_download(c, out);
+  if (timing) {
+    const auto t3 = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "[trpa] predict_batch: upload %.3f ms, run %.3f ms, download %.3f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3));
+  }
+  return rc;
 }
 
 // ----------------------------------------------------------------------- lower-level entry points

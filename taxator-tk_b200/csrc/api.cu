@@ -35,11 +35,13 @@ int alu_probe_ops_per_iter();
 
 // host-side parallel loop over [0, n) in contiguous blocks (batch preparation is memory bound and
 // would otherwise cost more than the H2D copy of a 5 M-candidate batch)
+// `work`: items the whole loop touches (a table of 50 k segments x 30 records is worth 16 threads, 50 k bare items
+// are not)
 template <class F>
-static void parallel_blocks(size_t n, const F& f) {
+static void parallel_blocks(size_t n, size_t work, const F& f) {
   unsigned T = std::thread::hardware_concurrency();
   if (T > 16) T = 16;
-  if (T < 2 || n < 65536) { f(0, n); return; }
+  if (T < 2 || n < 64 || work < 262144) { f(0, n); return; }
   std::vector<std::thread> th;
   const size_t per = (n + T - 1) / T;
   for (unsigned t = 0; t < T; ++t) {
@@ -179,7 +181,6 @@ struct trpa_ctx {
   u32 band_k0 = 0;            // test hook: forced initial threshold (0 = planned), exercises the retry loop
   u32 la_cap = 300000;        // pairs per round the automatic look-ahead aims for (measured: C2 +10 %, C1 2.4x vs none)
   u32 la_max = 32;            // largest automatic look-ahead budget per segment and round
-  int tax_smem = 1;           // tuning hook: small taxonomies are cached in shared memory by decide_kernel
   int force_shape = -1;       // tuning hook: (lidx * kNumW + widx) forced for every pair, -1 = planner
   PlanParams plan;            // hint margin + cost model of the shape planner (tuning hooks)
   u32 plan_lanes = 0;         // tuning hook: weight of a pair's latency against the summed lane-time in the shape planner (0 = automatic, see bucket_pairs3)
@@ -191,21 +192,7 @@ struct trpa_ctx {
 namespace trpa {
 
 // ------------------------------------------------------------------------------------ kernels
-// tax_nodes > 0: the taxonomy (13 B per node) fits the block's dynamic shared memory and is copied there first.
-// The state machine is one divergent thread per segment whose time is a chain of dependent loads, most of them the
-// parent / left / right walks of getLCA (taxonomyinterface.cpp:67-77): from shared memory a hop costs ~30 cycles
-// instead of an L2 round trip.  Pruned taxonomies of real refpacks that do not fit stay in global memory.
-__global__ void decide_kernel(Batch B, u32 seg_begin, u32 seg_end, u32 tax_nodes) {
-  extern __shared__ u32 tax_smem[];
-  if (tax_nodes) {
-    u32* sp = tax_smem; u32* sl = sp + tax_nodes; u32* sr = sl + tax_nodes;
-    uint8_t* sd = reinterpret_cast<uint8_t*>(sr + tax_nodes);
-    for (u32 i = threadIdx.x; i < tax_nodes; i += blockDim.x) {
-      sp[i] = B.tax.parent[i]; sl[i] = B.tax.left[i]; sr[i] = B.tax.right[i]; sd[i] = B.tax.depth[i];
-    }
-    __syncthreads();
-    B.tax.parent = sp; B.tax.left = sl; B.tax.right = sr; B.tax.depth = sd;
-  }
+__global__ void decide_kernel(Batch B, u32 seg_begin, u32 seg_end) {
   const u32 s = seg_begin + blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= seg_end) return;
   if (B.st[s].phase == PH_DONE) return;
@@ -213,7 +200,6 @@ __global__ void decide_kernel(Batch B, u32 seg_begin, u32 seg_end, u32 tax_nodes
   M.advance();
   if (B.st[s].phase != PH_DONE) atomicAdd(&B.counters[CN_ACTIVE], 1u);
 }
-constexpr u32 kDecideTaxSmemNodes = 3400;   // 13 B x 3400 = 44.2 KB: below the 48 KB a kernel gets without opting in
 
 __global__ void init_state_kernel(SegState* st, u32 n) {
   const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -532,7 +518,6 @@ int trpa_set_tuning(trpa_ctx* c, const char* key, int64_t value) {
   else if (k == "cost_step") c->plan.step = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
   else if (k == "cost_setup") c->plan.setup = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
   else if (k == "cost_setup_w") c->plan.setup_w = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 16));
-  else if (k == "tax_smem") c->tax_smem = value ? 1 : 0;
   else if (k == "wedge_max_k") c->plan.wedge_max_k = (u32)std::max<int64_t>(64, std::min<int64_t>(value, 1 << 22));
   else if (k == "wedge_hint_s8") c->plan.wedge_hint_s8 = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 15));
   else if (k == "wedge_hint_max_k") c->plan.wedge_hint_max_k = (u32)std::max<int64_t>(64, std::min<int64_t>(value, 1 << 22));
@@ -744,7 +729,7 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
     struct Bad { size_t seg; int code; };
     std::mutex bad_mutex;
     Bad first_bad{~(size_t)0, 0};
-    parallel_blocks(n_segs, [&](size_t b, size_t e) {
+    parallel_blocks(n_segs, (size_t)n_segs + n_cands, [&](size_t b, size_t e) {
       int code = 0;
       size_t at = 0;
       for (size_t s = b; s < e && !code; ++s) {
@@ -863,10 +848,7 @@ enum PipeState { PS_IDLE = 0, PS_WAIT_DECIDE, PS_WAIT_PLAN, PS_DONE };
 // decide kernel of the pipe's chunk + read-back of the round counters (asynchronous)
 static int enqueue_decide(trpa_ctx* c, Pipe& P) {
   const int ev = begin_event(P, EV_DECIDE);
-  {
-    const u32 tn = (c->n_nodes <= kDecideTaxSmemNodes && c->tax_smem) ? c->n_nodes : 0u;
-    decide_kernel<<<(P.se - P.sb + 63) / 64, 64, tn ? (size_t)tn * 13u + 16u : 0, P.stream>>>(P.B, P.sb, P.se, tn);
-  }
+  decide_kernel<<<(P.se - P.sb + 63) / 64, 64, 0, P.stream>>>(P.B, P.sb, P.se);
   CK(cudaGetLastError());
   end_event(P, ev);
   c->prof.launches_decide++;

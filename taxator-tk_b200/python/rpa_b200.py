@@ -17,7 +17,9 @@ RESULT_DTYPE = np.dtype([("qrstart", "<u4"), ("qrstop", "<u4"), ("lower_node", "
                          ("rtax_node", "<u4"), ("support", "<u4"), ("ival", "<f4"), ("signal", "<f4"),
                          ("n_pass0", "<u4"), ("n_pass1", "<u4"), ("n_pass2", "<u4"), ("kind", "<u4"),
                          ("cells", "<u8")])
-assert CAND_DTYPE.itemsize == 36 and SEG_DTYPE.itemsize == 16 and RESULT_DTYPE.itemsize == 56
+TRACE_DTYPE = np.dtype([("seg", "<u4"), ("a", "<u4"), ("b", "<u4"), ("r0", "<i4"), ("r1", "<i4"), ("len_a", "<u4"),
+                        ("len_b", "<u4"), ("self", "<u4")])
+assert CAND_DTYPE.itemsize == 36 and SEG_DTYPE.itemsize == 16 and RESULT_DTYPE.itemsize == 56 and TRACE_DTYPE.itemsize == 32
 
 
 class Profile(ctypes.Structure):
@@ -184,6 +186,18 @@ class Context:
         if out is None:
             out = np.zeros(self._n_segs, RESULT_DTYPE)
         self._ck(self.L.trpa_batch_download(self.h, _p(out)))
+        return out
+
+    def set_trace(self, on):
+        self._ck(self.L.trpa_set_trace(self.h, ctypes.c_int(int(on))))
+
+    def batch_trace(self):
+        """The alignments the last batch_run consumed (TRACE_DTYPE), ordered by segment, reference order inside."""
+        n = ctypes.c_uint64(0)
+        self._ck(self.L.trpa_batch_trace(self.h, None, ctypes.c_uint64(0), ctypes.byref(n)))
+        out = np.zeros(n.value, TRACE_DTYPE)
+        if n.value:
+            self._ck(self.L.trpa_batch_trace(self.h, _p(out), ctypes.c_uint64(n.value), ctypes.byref(n)))
         return out
 
     def batch_results_dev(self):

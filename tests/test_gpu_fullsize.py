@@ -37,7 +37,10 @@ def test_c2_full_size_execution_invariance(ctx):
         cells = int(base["cells"].sum())
         # the band executes a fraction of the reference's cells, and its thresholds are true upper bounds
         assert 0 < prof["cells_edit_distance"] < 0.3 * cells
-        assert prof["band_retries"] <= 10
+        # thresholds from the mismatch profile are true upper bounds: the only re-runs are wedges whose certificate
+        # failed (a fraction of a per mille of the pairs)
+        assert prof["band_retries"] - prof["wedge_failures"] <= 10
+        assert prof["wedge_failures"] <= 0.001 * prof["pairs"]
         # 1. no look-ahead, two pipelines, an arena that forces several chunks
         ctx.set_lookahead(0)
         ctx.set_tuning("pipes", 2)

@@ -40,6 +40,36 @@ def test_log_writer_detects_a_wrong_trace(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", ["nt_small", "aa_300", "nt_mixed"])
+def test_gpu_trace_equals_host_machine_trace(ctx, case):
+    """trpa_set_trace / trpa_batch_trace: the decide kernel records exactly the alignments (pair, raw integers, lengths,
+    self scores) that the host-compiled state machine consumes with the oracle's alignments, in the same order -- with
+    and without look-ahead, and tracing never changes a result."""
+    import golden_util as gu
+    import numpy as np
+    fd = ol.FlatData(gu.case_data(case))
+    want_res, _, want = ol.host_machine_predict(fd, want_trace=True)
+    ctx.load_taxonomy(fd.parent, fd.left, fd.right, fd.depth, 0)
+    alpha = 1 if fd.protein else 0
+    ctx.load_store(0, alpha, fd.q_chars, fd.q_off, fd.q_len)
+    ctx.load_store(1, alpha, fd.r_chars, fd.r_off, fd.r_len)
+    plain = ctx.predict_batch(fd.segs, fd.cands)
+    try:
+        ctx.set_trace(1)
+        for la in (-1, 0):
+            ctx.set_lookahead(la)
+            got_res = ctx.predict_batch(fd.segs, fd.cands)
+            got = ctx.batch_trace()
+            assert ol.results_equal(plain, got_res) == [] and ol.results_equal(want_res, got_res) == []
+            assert len(got) == len(want) == int((got_res["n_pass0"] + got_res["n_pass1"] + got_res["n_pass2"]).sum())
+            for f in got.dtype.names:
+                assert np.array_equal(got[f], want[f]), f
+    finally:
+        ctx.set_trace(0)
+        ctx.set_lookahead(-1)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("case", sorted(lu.LOG_CASES))
 def test_cli_verbose_log_matches_reference(case, tmp_path):
     exe = os.path.join(ol.ROOT, "taxator-tk_b200", "bin", "taxator-b200")

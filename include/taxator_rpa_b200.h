@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TRPA_ABI_VERSION 8
+#define TRPA_ABI_VERSION 9
 
 #define TRPA_OK 0
 #define TRPA_ERR_CUDA (-1)
@@ -184,6 +184,12 @@ int trpa_batch_download(trpa_ctx* ctx, trpa_result* out);
  * in the reference's order.  Results never depend on tracing. */
 int trpa_set_trace(trpa_ctx* ctx, int on);
 int trpa_batch_trace(trpa_ctx* ctx, trpa_trace_entry* out, uint64_t cap, uint64_t* n);
+
+/* Page-locked host memory for the tables a caller hands to trpa_predict_batch (DMA straight from the caller's buffers
+ * instead of a staged copy).  Portable across contexts / devices.  Without a CUDA device the memory is ordinary host
+ * memory (only the transfer speed differs; compute entry points still fail).  Thread-safe. */
+void* trpa_host_alloc(uint64_t bytes);
+void trpa_host_free(void* p);
 
 /* Multi-GPU (taxator.cpp:181-210 parallelises over record sets only): segments are independent, so a batch is cut
  * into `world` contiguous shards, one per GPU / context, and the fixed-size result records are concatenated in

@@ -1044,6 +1044,29 @@ int trpa_batch_download(trpa_ctx* c, trpa_result* out) {
   return 0;
 }
 
+// ---- page-locked host buffers
+static std::mutex g_host_mutex;
+static std::vector<void*> g_host_plain;   // allocations that fell back to ordinary memory (no CUDA device)
+
+void* trpa_host_alloc(uint64_t bytes) {
+  if (bytes == 0) bytes = 1;
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) return p;
+  cudaGetLastError();
+  p = malloc(bytes);
+  if (p) { std::lock_guard<std::mutex> l(g_host_mutex); g_host_plain.push_back(p); }
+  return p;
+}
+void trpa_host_free(void* p) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> l(g_host_mutex);
+    auto it = std::find(g_host_plain.begin(), g_host_plain.end(), p);
+    if (it != g_host_plain.end()) { g_host_plain.erase(it); free(p); return; }
+  }
+  cudaFreeHost(p);
+}
+
 int trpa_set_trace(trpa_ctx* c, int on) {
   if (!c) { set_error("null ctx"); return TRPA_ERR_ARG; }
   c->trace_on = on ? 1 : 0;

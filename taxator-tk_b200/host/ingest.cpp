@@ -484,6 +484,9 @@ uint64_t run_prediction_fast_blocks(FILE* in, const SeqIdMapping& mapping, const
   FastIngest ingest(in, mapping, tax, refs, q_store, opt);
   typedef std::unique_ptr<FlatBlock> BlockPtr;
   BoundedQueue<BlockPtr> parsed(2), placed(2);
+  // written blocks go back to the producer: their (page-locked) tables keep their capacity
+  std::mutex free_m;
+  std::vector<BlockPtr> free_blocks;
   std::mutex err_m;
   std::exception_ptr err;
   auto fail = [&](std::exception_ptr e) {
@@ -495,7 +498,12 @@ uint64_t run_prediction_fast_blocks(FILE* in, const SeqIdMapping& mapping, const
   std::thread producer([&]() {
     try {
       for (;;) {
-        BlockPtr b(new FlatBlock());
+        BlockPtr b;
+        {
+          std::lock_guard<std::mutex> l(free_m);
+          if (!free_blocks.empty()) { b = std::move(free_blocks.back()); free_blocks.pop_back(); }
+        }
+        if (!b) b.reset(new FlatBlock());
         const auto t0 = Clock::now();
         const bool more = ingest.next(*b);
         st.ingest_s += secs(t0, Clock::now());
@@ -523,6 +531,10 @@ uint64_t run_prediction_fast_blocks(FILE* in, const SeqIdMapping& mapping, const
             stats->alignments += (uint64_t)r.n_pass0 + r.n_pass1 + r.n_pass2;
             stats->cells += r.cells;
           }
+        }
+        {
+          std::lock_guard<std::mutex> l(free_m);
+          if (free_blocks.size() < 8) free_blocks.push_back(std::move(b));
         }
         b.reset();
       }

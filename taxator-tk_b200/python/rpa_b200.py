@@ -49,7 +49,7 @@ EXPORTS = ["trpa_abi_version", "trpa_last_error", "trpa_create", "trpa_destroy",
            "trpa_set_arena_bytes", "trpa_set_lookahead", "trpa_set_band", "trpa_set_tuning", "trpa_profile_reset", "trpa_profile_get", "trpa_load_taxonomy", "trpa_load_store", "trpa_store_info", "trpa_export_store", "trpa_load_store_packed",
            "trpa_predict_batch", "trpa_batch_upload", "trpa_batch_run", "trpa_batch_download",
            "trpa_predict_lca_batch", "trpa_edit_distance_batch", "trpa_protein_align_batch", "trpa_fetch_segments", "trpa_lca_batch",
-           "trpa_int_alu_peak", "trpa_shard_bounds", "trpa_batch_results_dev", "trpa_bin_batch", "trpa_set_trace", "trpa_batch_trace"]
+           "trpa_int_alu_peak", "trpa_shard_bounds", "trpa_batch_results_dev", "trpa_bin_batch", "trpa_set_trace", "trpa_batch_trace", "trpa_host_alloc", "trpa_host_free"]
 
 _lib = None
 

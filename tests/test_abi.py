@@ -25,7 +25,7 @@ def test_header_symbols_exported():
     assert len(syms) >= 20
     for s in syms:
         assert hasattr(L, s), s
-    assert L.trpa_abi_version() == 8
+    assert L.trpa_abi_version() == 9
 
 
 def test_binding_lists_all_exports():

@@ -186,8 +186,9 @@ int trpa_set_trace(trpa_ctx* ctx, int on);
 int trpa_batch_trace(trpa_ctx* ctx, trpa_trace_entry* out, uint64_t cap, uint64_t* n);
 
 /* Page-locked host memory for the tables a caller hands to trpa_predict_batch (DMA straight from the caller's buffers
- * instead of a staged copy).  Portable across contexts / devices.  Without a CUDA device the memory is ordinary host
- * memory (only the transfer speed differs; compute entry points still fail).  Thread-safe. */
+ * instead of a staged copy).  Portable across contexts / devices; allocated under the device of the process's first
+ * context.  Before any context exists, or without a CUDA device, the memory is ordinary host memory (only the transfer
+ * speed differs; compute entry points still fail).  Thread-safe. */
 void* trpa_host_alloc(uint64_t bytes);
 void trpa_host_free(void* p);
 

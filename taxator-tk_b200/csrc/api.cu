@@ -4,6 +4,7 @@
 // There is no CPU fallback: every compute entry point needs a CUDA device.
 // Compile with --fmad=false (decision arithmetic must match the reference's IEEE float/double ops).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <mutex>
 #include <cstdio>
@@ -21,6 +22,7 @@
 namespace trpa {
 
 static thread_local std::string g_error;
+static std::atomic<int> g_first_device{-1};   // device of the first context of this process (trpa_create)
 void set_error(const std::string& s) { g_error = s; }
 int alu_probe_ops_per_iter();
 
@@ -459,6 +461,7 @@ trpa_ctx* trpa_create(int device, void* cuda_stream) {
   if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
   trpa_ctx* c = new trpa_ctx();
   c->device = device;
+  { int none = -1; g_first_device.compare_exchange_strong(none, device); }
   memset(&c->prof, 0, sizeof(c->prof));
   if (c->pipe[0].init((cudaStream_t)cuda_stream)) { delete c; return nullptr; }
   c->stream = c->pipe[0].stream;
@@ -1051,7 +1054,10 @@ static std::vector<void*> g_host_plain;   // allocations that fell back to ordin
 void* trpa_host_alloc(uint64_t bytes) {
   if (bytes == 0) bytes = 1;
   void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) return p;
+  // allocate under a device this process already uses: a thread that never touched CUDA (the ingest thread of the
+  // CLI) would otherwise create a context on device 0, which the caller may not own
+  const int dev = g_first_device.load();
+  if (dev >= 0 && cudaSetDevice(dev) == cudaSuccess && cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) return p;
   cudaGetLastError();
   p = malloc(bytes);
   if (p) { std::lock_guard<std::mutex> l(g_host_mutex); g_host_plain.push_back(p); }

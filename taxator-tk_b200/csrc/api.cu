@@ -582,7 +582,7 @@ int trpa_load_store(trpa_ctx* c, int store, int alphabet, const char* chars, con
     // SeqDesc.woff of the packing descriptor is 32 bit; stores beyond 137 Gbases need a wider layout
     set_error("nucleotide store larger than 2^32 words is not supported yet"); return TRPA_ERR_ARG;
   }
-  DevBuf<uint8_t> d_chars; DevBuf<u64> d_off;
+  ScopedBuf<uint8_t> d_chars; ScopedBuf<u64> d_off;
   if (d_chars.ensure(nchars + 1) || d_off.ensure(n_seq + 1) || S.woff.ensure(n_seq + 1) || S.len.ensure(n_seq + 1)) return TRPA_ERR_NOMEM;
   CK(cudaMemcpyAsync(d_chars.p, chars, nchars, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(d_off.p, off, 8ull * n_seq, cudaMemcpyHostToDevice, c->stream));
@@ -591,7 +591,7 @@ int trpa_load_store(trpa_ctx* c, int store, int alphabet, const char* chars, con
   if (alphabet == TRPA_ALPHA_NT) {
     std::vector<SeqDesc> sd(n_seq);
     for (u32 i = 0; i < n_seq; ++i) sd[i] = SeqDesc{(u32)woff[i], len[i], 0, 0};
-    DevBuf<SeqDesc> d_sd;
+    ScopedBuf<SeqDesc> d_sd;
     if (d_sd.ensure(n_seq + 1) || S.planes.ensure(words + 2) || S.nplane.ensure(words + 2)) return TRPA_ERR_NOMEM;
     CK(cudaMemsetAsync(S.planes.p, 0, (words + 2) * sizeof(uint2), c->stream));
     CK(cudaMemsetAsync(S.nplane.p, 0, (words + 2) * sizeof(u32), c->stream));
@@ -1122,7 +1122,7 @@ int trpa_predict_batch(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, c
 
 // ----------------------------------------------------------------------- lower-level entry points
 static int upload_table(trpa_ctx* c, const char* chars, const uint64_t* off, const uint32_t* len, uint32_t n_seq,
-                        DevBuf<uint8_t>& d_chars, DevBuf<u64>& d_off, u64* nchars_out) {
+                        ScopedBuf<uint8_t>& d_chars, ScopedBuf<u64>& d_off, u64* nchars_out) {
   u64 nchars = 0;
   for (u32 i = 0; i < n_seq; ++i) nchars = std::max<u64>(nchars, off[i] + len[i]);
   if (d_chars.ensure(nchars + 1) || d_off.ensure(n_seq + 1)) return TRPA_ERR_NOMEM;
@@ -1140,15 +1140,15 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   if (n_pairs == 0) return 0;
   for (u32 k = 0; k < n_pairs; ++k)
     if (pair_a[k] >= n_seq || pair_b[k] >= n_seq) { set_error("pair index out of range"); return TRPA_ERR_ARG; }
-  DevBuf<uint8_t> d_chars; DevBuf<u64> d_off; u64 nchars = 0;
+  ScopedBuf<uint8_t> d_chars; ScopedBuf<u64> d_off; u64 nchars = 0;
   int rc = upload_table(c, chars, off, len, n_seq, d_chars, d_off, &nchars);
   if (rc) return rc;
   std::vector<SeqDesc> sd(n_seq);
   u64 words = 0; u32 max_len = 0;
   for (u32 i = 0; i < n_seq; ++i) { sd[i] = SeqDesc{(u32)words, len[i], 0, 0}; words += ((u64)len[i] + 31) / 32; max_len = std::max(max_len, len[i]); }
   if (words >= 0xffffffffull) { set_error("table too large"); return TRPA_ERR_ARG; }
-  DevBuf<SeqDesc> d_sd; DevBuf<uint2> planes, codes; DevBuf<u32> nplane; DevBuf<PairDesc> d_pairs, d_sorted; DevBuf<int32_t> d_out;
-  DevBuf<u32> d_cnt;
+  ScopedBuf<SeqDesc> d_sd; ScopedBuf<uint2> planes, codes; ScopedBuf<u32> nplane; ScopedBuf<PairDesc> d_pairs, d_sorted; ScopedBuf<int32_t> d_out;
+  ScopedBuf<u32> d_cnt;
   if (d_sd.ensure(n_seq + 1) || planes.ensure(words + 2) || codes.ensure(words + 2) || nplane.ensure(words + 2) || d_pairs.ensure(n_pairs) ||
       d_sorted.ensure(n_pairs) || d_out.ensure(n_pairs) || d_cnt.ensure(kNumCounters))
     return TRPA_ERR_NOMEM;
@@ -1156,7 +1156,7 @@ int trpa_edit_distance_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   CK(cudaMemsetAsync(planes.p, 0, (words + 2) * sizeof(uint2), c->stream));
   CK(cudaMemsetAsync(nplane.p, 0, (words + 2) * sizeof(u32), c->stream));
   // flags live inside the descriptor table (3rd u32 of each 16-byte entry): pass a strided view
-  DevBuf<u32> d_flags;
+  ScopedBuf<u32> d_flags;
   if (d_flags.ensure(n_seq + 1)) return TRPA_ERR_NOMEM;
   CK(cudaMemsetAsync(d_flags.p, 0, sizeof(u32) * (n_seq + 1), c->stream));
   CK(launch_pack_nt(d_chars.p, d_off.p, d_sd.p, n_seq, words, planes.p, nplane.p, d_flags.p, c->stream));
@@ -1209,14 +1209,14 @@ int trpa_protein_align_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   if (n_pairs == 0) return 0;
   for (u32 k = 0; k < n_pairs; ++k)
     if (pair_a[k] >= n_seq || pair_b[k] >= n_seq) { set_error("pair index out of range"); return TRPA_ERR_ARG; }
-  DevBuf<uint8_t> d_chars, d_codes; DevBuf<u64> d_off; u64 nchars = 0;
+  ScopedBuf<uint8_t> d_chars, d_codes; ScopedBuf<u64> d_off; u64 nchars = 0;
   int rc = upload_table(c, chars, off, len, n_seq, d_chars, d_off, &nchars);
   if (rc) return rc;
   if (nchars >= 0xffffffffull) { set_error("table too large"); return TRPA_ERR_ARG; }
   std::vector<SeqDesc> sd(n_seq);
   u32 max_len = 0;
   for (u32 i = 0; i < n_seq; ++i) { sd[i] = SeqDesc{(u32)off[i], len[i], 0, 0}; max_len = std::max(max_len, len[i]); }
-  DevBuf<SeqDesc> d_sd; DevBuf<PairDesc> d_pairs; DevBuf<int2> d_out;
+  ScopedBuf<SeqDesc> d_sd; ScopedBuf<PairDesc> d_pairs; ScopedBuf<int2> d_out;
   if (d_codes.ensure(nchars + 1) || d_sd.ensure(n_seq + 1) || d_pairs.ensure(n_pairs) || d_out.ensure(n_pairs)) return TRPA_ERR_NOMEM;
   CK(ensure_blosum_constant(c->device));
   CK(launch_aa_codes(d_chars.p, d_codes.p, nchars, c->stream));
@@ -1286,13 +1286,13 @@ int trpa_fetch_segments(trpa_ctx* c, const uint32_t* ref_seq, const uint32_t* st
   }
   if (total > out_capacity) { set_error("output buffer too small"); return TRPA_ERR_ARG; }
   if (units >= 0xffffffffull) { set_error("fetch too large"); return TRPA_ERR_ARG; }
-  DevBuf<SeqDesc> d_sd; DevBuf<StageReq> d_rq; DevBuf<uint8_t> d_out; DevBuf<u64> d_ooff;
+  ScopedBuf<SeqDesc> d_sd; ScopedBuf<StageReq> d_rq; ScopedBuf<uint8_t> d_out; ScopedBuf<u64> d_ooff;
   if (d_sd.ensure(n + 1) || d_rq.ensure(n + 1) || d_out.ensure(total + 16) || d_ooff.ensure(n + 1)) return TRPA_ERR_NOMEM;
   CK(cudaMemcpyAsync(d_sd.p, sd.data(), sizeof(SeqDesc) * n, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(d_rq.p, rq.data(), sizeof(StageReq) * n, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(d_ooff.p, out_off, 8ull * n, cudaMemcpyHostToDevice, c->stream));
   if (protein) {
-    DevBuf<uint8_t> stg;
+    ScopedBuf<uint8_t> stg;
     if (stg.ensure(units + 16)) return TRPA_ERR_NOMEM;
     CK(ensure_blosum_constant(c->device));
     CK(launch_stage_aa(d_rq.p, n, nullptr, nullptr, R.packed.p, R.woff.p, d_sd.p, stg.p, c->stream));
@@ -1302,7 +1302,7 @@ int trpa_fetch_segments(trpa_ctx* c, const uint32_t* ref_seq, const uint32_t* st
     CK(cudaStreamSynchronize(c->stream));
     stg.release();
   } else {
-    DevBuf<uint2> pl; DevBuf<u32> pn;
+    ScopedBuf<uint2> pl; ScopedBuf<u32> pn;
     if (pl.ensure(units + 2) || pn.ensure(units + 2)) return TRPA_ERR_NOMEM;
     CK(launch_stage_nt(d_rq.p, n, nullptr, nullptr, nullptr, R.planes.p, R.nplane.p, R.woff.p, d_sd.p, pl.p, pn.p, nullptr, c->stream));
     CK(launch_unstage_nt(d_sd.p, n, pl.p, pn.p, d_ooff.p, d_out.p, c->stream));
@@ -1462,7 +1462,7 @@ int trpa_lca_batch(trpa_ctx* c, const uint32_t* a, const uint32_t* b, uint32_t n
   if (use_device(c)) return TRPA_ERR_CUDA;
   for (u32 i = 0; i < n; ++i) if (a[i] >= c->n_nodes || b[i] >= c->n_nodes) { set_error("node out of range"); return TRPA_ERR_ARG; }
   if (n == 0) return 0;
-  DevBuf<u32> da, db, dout;
+  ScopedBuf<u32> da, db, dout;
   if (da.ensure(n) || db.ensure(n) || dout.ensure(n)) return TRPA_ERR_NOMEM;
   CK(cudaMemcpyAsync(da.p, a, 4ull * n, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(db.p, b, 4ull * n, cudaMemcpyHostToDevice, c->stream));
@@ -1477,7 +1477,7 @@ int trpa_lca_batch(trpa_ctx* c, const uint32_t* a, const uint32_t* b, uint32_t n
 int trpa_int_alu_peak(trpa_ctx* c, double* lane_ops_per_s) {
   if (!c || !lane_ops_per_s) { set_error("bad arguments"); return TRPA_ERR_ARG; }
   if (use_device(c)) return TRPA_ERR_CUDA;
-  DevBuf<u32> sink;
+  ScopedBuf<u32> sink;
   if (sink.ensure(4)) return TRPA_ERR_NOMEM;
   int blocks = 0, threads = 0;
   const int iters = 20000;

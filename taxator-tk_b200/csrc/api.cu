@@ -1056,7 +1056,8 @@ void* trpa_host_alloc(uint64_t bytes) {
   void* p = nullptr;
   // allocate under a device this process already uses: a thread that never touched CUDA (the ingest thread of the
   // CLI) would otherwise create a context on device 0, which the caller may not own
-  const int dev = g_first_device.load();
+  static const bool no_pinned = getenv("TRPA_NO_PINNED") != nullptr;   // A/B switch
+  const int dev = no_pinned ? -1 : g_first_device.load();
   if (dev >= 0 && cudaSetDevice(dev) == cudaSuccess && cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) return p;
   cudaGetLastError();
   p = malloc(bytes);

@@ -484,7 +484,7 @@ uint64_t run_prediction_fast_blocks(FILE* in, const SeqIdMapping& mapping, const
   FastIngest ingest(in, mapping, tax, refs, q_store, opt);
   typedef std::unique_ptr<FlatBlock> BlockPtr;
   BoundedQueue<BlockPtr> parsed(2), placed(2);
-  // written blocks go back to the producer: their (page-locked) tables keep their capacity
+  // written blocks go back to the producer: their tables keep their capacity
   std::mutex free_m;
   std::vector<BlockPtr> free_blocks;
   std::mutex err_m;

@@ -53,32 +53,17 @@ struct SegMeta {
   uint32_t any_active;   // 0: every record of the set is masked (n == 0)
 };
 
-// std::allocator over page-locked host memory (trpa_host_alloc): the tables of a block go to the GPU by DMA straight
-// from these vectors.  Blocks are recycled (run_prediction_fast_blocks), so the allocations happen a few times per run.
-template <class T>
-struct PinnedAllocator {
-  typedef T value_type;
-  PinnedAllocator() {}
-  template <class U> PinnedAllocator(const PinnedAllocator<U>&) {}
-  T* allocate(size_t n) {
-    void* p = trpa_host_alloc((uint64_t)n * sizeof(T));
-    if (!p) throw std::bad_alloc();
-    return static_cast<T*>(p);
-  }
-  void deallocate(T* p, size_t) { trpa_host_free(p); }
-  template <class U> bool operator==(const PinnedAllocator<U>&) const { return true; }
-  template <class U> bool operator!=(const PinnedAllocator<U>&) const { return false; }
-};
-template <class T> using PinnedVector = std::vector<T, PinnedAllocator<T>>;
-
 // one block of the alignment stream, flattened
 struct FlatBlock {
   std::vector<char> text;            // owns what SegMeta::qid points into
-  PinnedVector<trpa_segment> segs;
-  PinnedVector<trpa_candidate> cands;
-  PinnedVector<double> evalue;       // one per candidate (IngestOptions::want_evalue)
+  // Plain pageable vectors.  Page-locked blocks (trpa_host_alloc) were measured and dropped: cudaHostAlloc / FreeHost of
+  // the ~60 MB tables cost 0.3-0.7 s per run and stall the GPU stage while they hold the driver lock, against ~16 ms of
+  // staged copy saved per 100 k-segment block (scripts/cli_timing_probe.py: 100 k segments 2.4-2.6 s vs 1.73 s wall).
+  std::vector<trpa_segment> segs;
+  std::vector<trpa_candidate> cands;
+  std::vector<double> evalue;        // one per candidate (IngestOptions::want_evalue)
   std::vector<SegMeta> meta;
-  PinnedVector<trpa_result> res;
+  std::vector<trpa_result> res;
   uint64_t first_line = 0;           // line number (1-based) of the block's first line
 };
 

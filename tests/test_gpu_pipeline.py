@@ -122,3 +122,37 @@ def test_packed_store_roundtrip(ctx):
         a, woff, lens, payload = packs[1]
         with pytest.raises(rpa_b200.TrpaError):
             ctx.load_store_packed(1, a, woff + np.uint64(1), lens, payload)
+
+
+def test_page_locked_host_tables(ctx):
+    """trpa_host_alloc / trpa_host_free: tables in page-locked memory of the library go through trpa_predict_batch like any
+    other host buffer (same results), and the memory is usable as ordinary host memory."""
+    import ctypes
+    import rpa_b200
+    fd = ol.FlatData(gu.case_data("nt_small"))
+    ctx.load_taxonomy(fd.parent, fd.left, fd.right, fd.depth, 0)
+    ctx.load_store(0, 0, fd.q_chars, fd.q_off, fd.q_len)
+    ctx.load_store(1, 0, fd.r_chars, fd.r_off, fd.r_len)
+    want = ctx.predict_batch(fd.segs, fd.cands)
+    L = ctx.L
+    L.trpa_host_alloc.restype = ctypes.c_void_p
+    L.trpa_host_alloc.argtypes = [ctypes.c_uint64]
+    L.trpa_host_free.argtypes = [ctypes.c_void_p]
+    L.trpa_host_free.restype = None
+    bufs = []
+    try:
+        def pinned_copy(a):
+            p = L.trpa_host_alloc(a.nbytes)
+            assert p
+            bufs.append(p)
+            v = np.frombuffer((ctypes.c_uint8 * a.nbytes).from_address(p), dtype=a.dtype)
+            v[:] = a
+            return v
+        segs = pinned_copy(np.ascontiguousarray(fd.segs, rpa_b200.SEG_DTYPE))
+        cands = pinned_copy(np.ascontiguousarray(fd.cands, rpa_b200.CAND_DTYPE))
+        out = pinned_copy(np.zeros(len(fd.segs), rpa_b200.RESULT_DTYPE))
+        got = ctx.predict_batch_into(segs, cands, out)
+        assert ol.results_equal(want, got) == []
+    finally:
+        for p in bufs:
+            L.trpa_host_free(p)

@@ -128,6 +128,7 @@ def test_page_locked_host_tables(ctx):
     """trpa_host_alloc / trpa_host_free: tables in page-locked memory of the library go through trpa_predict_batch like any
     other host buffer (same results), and the memory is usable as ordinary host memory."""
     import ctypes
+    import golden_util as gu
     import rpa_b200
     fd = ol.FlatData(gu.case_data("nt_small"))
     ctx.load_taxonomy(fd.parent, fd.left, fd.right, fd.depth, 0)

@@ -818,6 +818,16 @@ def main():
                 "kernel_ms_per_step": k_ms / args.steps, "kernel_share_of_step": (k_ms / args.steps) / ms_step}
     if not fd.protein and peak:
         roofline["frac_r01_constant"] = roofline["frac"] * ALU_OPS_PER_WORDSTEP_R01 / ALU_OPS_PER_WORDSTEP
+        # Round 2 narrows the wedge further (fewer executed cells for the same integers), which LOWERS `frac` (per-step
+        # overheads are paid on fewer cells) while the step gets faster.  For a like-for-like reading against round 1:
+        # the cells round 1's band executed on this workload (0.1333 of the algorithmic cells on C2) over
+        # this build's kernel time.
+        if args.workload == "c2" and cells_step:
+            r1_cells = 0.1333 * cells_step * args.steps
+            roofline["frac_at_round1_band"] = r1_cells / (k_ms / 1e3) / 1e9 / peak
+            roofline["frac_note"] = ("frac = executed cells / kernel time / peak; this build executes %.4f of the algorithmic cells "
+                                     "(round 1: 0.1333), frac_at_round1_band counts round 1's executed cells over this build's time"
+                                     % (executed_cells / (cells_step * args.steps)))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

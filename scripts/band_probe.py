@@ -31,8 +31,7 @@ for L, npairs, div in cases:
     pb = rng.integers(0, nseq, npairs).astype(np.uint32)
     cells = float(L) * L * npairs
     ref = None
-    for name, ver, band, wedge in (("myers2 full", 2, 1, 0), ("myers3 full", 3, 0, 0), ("myers3 band", 3, 1, 0), ("myers3 wedge", 3, 1, 1)):
-        ctx.set_tuning("myers_version", ver)
+    for name, band, wedge in (("full matrix", 0, 0), ("band", 1, 0), ("band + wedge", 1, 1)):
         ctx.set_tuning("wedge", wedge)
         ctx.set_band(band)
         ctx.profile_reset()
@@ -45,6 +44,5 @@ for L, npairs, div in cases:
         print("L=%d pairs=%d div=%.2f %-12s %8.2f ms  %9.1f GCUPS algorithmic  executed %.3f  (%7.1f GCUPS executed) retries %d"
               % (L, npairs, div, name, ms, cells / ms / 1e6, ex / cells if ex else 1.0, (ex or cells) / ms / 1e6,
                  p["band_retries"] // 3), flush=True)
-ctx.set_tuning("myers_version", 3)
 ctx.set_tuning("wedge", 1)
 ctx.set_band(1)

@@ -34,5 +34,27 @@ def main():
                 print(case, variant, p.stdout.count(b"\n"), "lines;", p.stderr.decode().replace("\n", " | ")[:160])
 
 
+def pipeline():
+    """`taxator -p 1 | binner`: the reference's two programs piped (record order = the order taxator prints)."""
+    taxator = os.path.join(ROOT, "oracle", "_ref", "taxator")
+    binary = os.path.join(ROOT, "oracle", "_ref", "binner")
+    for case in ("nt_small", "nt_1kb"):
+        data = gu.case_data(case)
+        with tempfile.TemporaryDirectory() as tmp:
+            bu.deep_taxonomy_files(data, tmp)
+            env = dict(os.environ, TAXATORTK_TAXONOMY_NCBI=tmp)
+            with open(os.path.join(tmp, "alignments.tsv"), "rb") as fin:
+                gff = subprocess.run([taxator, "-a", "rpa", "-g", "mapping.tax", "-q", "query.fna", "-f", "ref.fna", "-i", "ref.fna.fai",
+                                      "-p", "1", "-x", "0.5", "-o", "0"], cwd=tmp, env=env, stdin=fin, stdout=subprocess.PIPE,
+                                     stderr=subprocess.DEVNULL, check=True).stdout
+            for variant in ("default", "glob10"):
+                p = subprocess.run([binary, "-n", "sample_" + case, "-l", os.path.join(tmp, "binning.log")] + bu.VARIANTS[variant][0],
+                                   cwd=tmp, env=env, input=gff, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+                assert p.returncode == 0, p.stderr.decode()[-500:]
+                open(bu.golden_path(case, "pipeline_" + variant), "wb").write(p.stdout)
+                print("pipeline", case, variant, p.stdout.count(b"\n"), "lines")
+
+
 if __name__ == "__main__":
     main()
+    pipeline()

@@ -197,3 +197,26 @@ def test_binner_cli_matches_reference_bytes(case, tmp_path):
                        input=("".join(gu.golden_lines(case)[half:])).encode(), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert p.returncode == 0, p.stderr.decode()
     assert p.stdout == open(bu.golden_path(case, "default"), "rb").read()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["nt_small", "nt_1kb"])
+def test_taxator_b200_piped_into_binner_b200_matches_reference_pipeline(case, tmp_path):
+    """`taxator-b200 | binner-b200` against `taxator -p 1 | binner` of the reference (tests/golden/binner_<case>_pipeline_*.tsv):
+    the same bytes, line order included -- both taxators print their records in input order."""
+    taxator = os.path.join(ol.ROOT, "taxator-tk_b200", "bin", "taxator-b200")
+    binner = os.path.join(ol.ROOT, "taxator-tk_b200", "bin", "binner-b200")
+    data = gu.case_data(case)
+    d = str(tmp_path)
+    bu.deep_taxonomy_files(data, d)
+    env = dict(os.environ, TAXATORTK_TAXONOMY_NCBI=d)
+    with open(os.path.join(d, "alignments.tsv"), "rb") as fin:
+        p = subprocess.run([taxator, "-a", "rpa", "-g", "mapping.tax", "-q", "query.fna", "-f", "ref.fna", "-i", "ref.fna.fai"], cwd=d, env=env,
+                           stdin=fin, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0, p.stderr.decode()
+    gff = p.stdout
+    for variant in ("default", "glob10"):
+        p = subprocess.run([binner, "-n", "sample_" + case, "-l", os.path.join(d, "binning.log")] + bu.VARIANTS[variant][0], cwd=d, env=env,
+                           input=gff, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert p.returncode == 0, p.stderr.decode()
+        assert p.stdout == open(bu.golden_path(case, "pipeline_" + variant), "rb").read(), variant

@@ -26,6 +26,76 @@ def log_case_data(case):
     return bench_subset.subset(gu.case_data(case), LOG_CASES[case])
 
 
+def special_case():
+    """(SynthData, masked flag per record in FILE order): the first 24 queries of nt_small with the corner cases of
+    predict() forced onto four single-segment queries -- n == 1 and n == 0 through masked records (hh:350-388), a
+    full-length 100 % top hit with a score tie (the shortcut of hh:431-472) and a 100 % hit that is not the best score
+    (the *ALN branch of hh:511-517)."""
+    d = log_case_data_n("nt_small", 24)
+    r = d.rec
+    n = len(r["q"])
+    masked = np.zeros(n, bool)
+    segs, _ = d.segments()
+    per_q = {}
+    for sg in segs:
+        per_q.setdefault(int(sg["query_seq"]), 0)
+        per_q[int(sg["query_seq"])] += 1
+    single = [q for q in sorted(per_q) if per_q[q] == 1 and int((r["q"] == q).sum()) >= 5][:4]
+    assert len(single) == 4
+    q0, q1, q2, q3 = single
+    idx = np.flatnonzero(r["q"] == q0)
+    masked[idx] = True
+    masked[idx[int(np.argmax(r["score"][idx]))]] = False            # n == 1
+    masked[r["q"] == q1] = True                                       # n == 0
+    for q, top in ((q2, True), (q3, False)):
+        idx = np.flatnonzero(r["q"] == q)
+        qs, qe = int(r["qstart"][idx].min()), int(r["qstop"][idx].max())
+        L = qe - qs + 1
+        order = idx[np.argsort(-r["score"][idx], kind="stable")]
+        k = order[0] if top else order[-1]
+        r["qstart"][k], r["qstop"][k] = qs, qe
+        r["alnlen"][k] = L; r["ident"][k] = L
+        if top:
+            r["score"][k] = 1e6
+            r["score"][order[1]] = 1e6                                # tie with the identical hit
+            r["score"][order[2]] = r["score"][order[3]]               # two records share the next score (upper node loop)
+    return d, masked
+
+
+def log_case_data_n(case, n):
+    import bench_subset
+    return bench_subset.subset(gu.case_data(case), n)
+
+
+def write_case_files(d, masked, outdir):
+    """The reference's input files with '*'-masked alignment lines (AlignmentRecord::isFiltered)."""
+    d.write_files(outdir)
+    r = d.rec
+    with open(os.path.join(outdir, "alignments.tsv"), "w") as f:
+        for k in range(len(r["q"])):
+            qi = r["q"][k]
+            f.write("%s%s\t%d\t%d\t%d\t%s\t%d\t%d\t%s\t0\t%d\t%d\n" % (
+                "*" if masked[k] else "", d.q_names[qi], r["qstart"][k], r["qstop"][k], len(d.q_seqs[qi]),
+                d.ref_names[r["r"][k]], r["rstart"][k], r["rstop"][k], repr(float(r["score"][k])), r["ident"][k], r["alnlen"][k]))
+
+
+def flat_with_masks(d, masked):
+    """ol.FlatData whose record sets are formed from ALL records and whose candidate table holds the unmasked ones."""
+    fd = ol.FlatData(d)
+    r = d.rec
+    nrec = len(r["q"])
+    order = np.lexsort((np.arange(nrec), r["qstop"], r["qstart"], r["q"]))
+    keep = ~masked[order]
+    csum = np.concatenate([[0], np.cumsum(keep)])
+    segs = fd.segs.copy()
+    for i, sg in enumerate(fd.segs):
+        b, c = int(sg["cand_begin"]), int(sg["cand_count"])
+        segs[i]["cand_begin"] = csum[b]
+        segs[i]["cand_count"] = csum[b + c] - csum[b]
+    fd.segs, fd.cands = segs, np.ascontiguousarray(fd.cands[keep])
+    return fd
+
+
 def blocks_of(text):
     """The log split into per-segment blocks ('ID\\t...' to the STATS line), CPU-time columns of STATS masked."""
     out, cur = [], []

@@ -28,6 +28,28 @@ def test_log_writer_reproduces_reference_log(case, spec_k, tmp_path):
         assert any("        " in b and "|" in b for b in ours)    # alignment renderings present
 
 
+def test_corner_cases_against_reference_log_and_gff3(tmp_path):
+    """n == 1 and n == 0 through masked records, the 100 % top-hit shortcut with a score tie, a 100 % hit that is not the
+    best score: GFF3 and log of the REAL reference (tests/golden/special.gff3, log_special.log.gz) vs the host-compiled
+    state machine + the product's log writer."""
+    import golden_util as gu
+    d, masked = lu.special_case()
+    fd = lu.flat_with_masks(d, masked)
+    res, _, trace = ol.host_machine_predict(fd, want_trace=True)
+    assert set(int(k) for k in res["kind"]) >= {0, 1, 2, 3}
+    out = str(tmp_path / "ours.log")
+    lu.write_log(fd, res, trace, out)
+    ours, want = lu.blocks_of(open(out).read()), lu.golden_blocks("special")
+    assert sorted(ours) == sorted(want)
+    text = "\n".join(ours)
+    assert "*ALN" in text and "current ref/lower node" in text and "NUMREF\t1\n" in text and "NUMREF\t0\n" in text
+    want_gff = [l for l in open(os.path.join(gu.GOLDEN, "special.gff3")).readlines() if not l.startswith("##")]
+    import gff3
+    taxids = [str(t) for t in d.tax_ids]
+    got_gff = gff3.render(res, fd.segs, d.q_names, fd.q_len, fd.parent, fd.depth, taxids)
+    assert got_gff == want_gff          # in input order: the n == 0 set inherits the ival of the record before it
+
+
 def test_log_writer_detects_a_wrong_trace(tmp_path):
     fd = ol.FlatData(lu.log_case_data("nt_small"))
     res, _, trace = ol.host_machine_predict(fd, want_trace=True)
@@ -91,3 +113,21 @@ def test_cli_verbose_log_matches_reference(case, tmp_path):
         ours = lu.blocks_of(open(os.path.join(d, "ours.log")).read())
         assert sorted(ours) == sorted(lu.golden_blocks(case))
     assert outs[0] == outs[1]
+
+
+@pytest.mark.gpu
+def test_cli_corner_cases_match_reference(tmp_path):
+    """taxator-b200 on an alignment file with masked records (n == 1, n == 0), the 100 % shortcut and a *ALN record:
+    GFF3 byte-identical to the real reference (incl. the ival an n == 0 set inherits) and the same log."""
+    import golden_util as gu
+    exe = os.path.join(ol.ROOT, "taxator-tk_b200", "bin", "taxator-b200")
+    data, masked = lu.special_case()
+    d = str(tmp_path)
+    lu.write_case_files(data, masked, d)
+    env = dict(os.environ, TAXATORTK_TAXONOMY_NCBI=d)
+    cmd = [exe, "-a", "rpa", "-g", "mapping.tax", "-q", "query.fna", "-f", "ref.fna", "-i", "ref.fna.fai", "-l", "ours.log"]
+    with open(os.path.join(d, "alignments.tsv"), "rb") as fin:
+        p = subprocess.run(cmd, cwd=d, env=env, stdin=fin, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0, p.stderr.decode()
+    assert p.stdout == open(os.path.join(gu.GOLDEN, "special.gff3"), "rb").read()
+    assert sorted(lu.blocks_of(open(os.path.join(d, "ours.log")).read())) == sorted(lu.golden_blocks("special"))

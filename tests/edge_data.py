@@ -12,9 +12,12 @@ def base(seed=11, protein=False, **kw):
     return ol.FlatData(synth.generate(synth.SynthConfig(**cfg)))
 
 
-def ranges_past_ends(protein):
+def ranges_past_ends(protein, far=True):
     """Reference coordinates beyond the stored sequence are clipped (sequencestorage.hh:353,
-    faidx.h:325-331); a start past the end yields an empty segment (distance = other length)."""
+    faidx.h:325-331); a start past the end yields an empty segment (distance = other length).
+    far=False leaves the start-past-the-end records out: on an EMPTY segment the real reference segfaults in the
+    nucleotide path and, in the protein path, gets INT_MIN from SeqAn for every alignment with an empty string, overflows
+    2 * INT_MIN and ends up with distance 0 (undefined behaviour; here an empty segment is at distance = the other length)."""
     fd = base(seed=21, protein=protein)
     rng = np.random.default_rng(5)
     c = fd.cands
@@ -23,18 +26,19 @@ def ranges_past_ends(protein):
     fwd = c["rstart"] <= c["rstop"]
     c["rstop"][pick & fwd] = (L[pick & fwd] + rng.integers(1, 500, int((pick & fwd).sum()))).astype(np.uint32)
     c["rstart"][pick & ~fwd] = (L[pick & ~fwd] + rng.integers(1, 500, int((pick & ~fwd).sum()))).astype(np.uint32)
-    far = rng.random(len(c)) < 0.03
+    far = (rng.random(len(c)) < 0.03) & bool(far)
     c["rstart"][far & fwd] = (L[far & fwd] + 10).astype(np.uint32)
     c["rstop"][far & fwd] = (L[far & fwd] + 200).astype(np.uint32)
     return fd
 
 
-def n_rich():
+def n_rich(letters=b"NRYKMnacgt-"):
+    """letters: what replaces 5 % of the query bases (the real reference's FASTA reader only accepts ACGTN in either case)."""
     fd = base(seed=22, frac_n=0.08)
     q = fd.q_chars.copy()
     rng = np.random.default_rng(1)
     m = rng.random(len(q)) < 0.05
-    q[m] = np.frombuffer(b"NRYKMnacgt-", np.uint8)[rng.integers(0, 11, int(m.sum()))]
+    q[m] = np.frombuffer(letters, np.uint8)[rng.integers(0, len(letters), int(m.sum()))]
     fd.q_chars = q
     fd.q_codes = ol.codes_of(q, False)
     return fd
@@ -77,3 +81,27 @@ def score_ties():
     c["identities"] = (c["identities"] // 16) * 16
     c["identities"] = np.minimum(c["identities"], c["alnlen"] - 1).astype(np.uint32)
     return fd
+
+
+def write_files_from_flat(fd, outdir):
+    """The files the reference reads, from the FLAT tables (the edge cases edit those, not the SynthData records):
+    taxonomy / mapping / reference FASTA of fd.d, query FASTA from fd.q_chars, one alignment line per candidate in table
+    order (inside a query that is (qstart, qstop, file order), which the reference's record-set generator keeps)."""
+    import os
+    d = fd.d
+    d.write_files(outdir)
+    q_seqs = [fd.q_chars[int(o):int(o) + int(l)] for o, l in zip(fd.q_off, fd.q_len)]
+    d._write_fasta(os.path.join(outdir, "query.fna"), d.q_names, q_seqs, fai=False)
+    with open(os.path.join(outdir, "alignments.tsv"), "w") as f:
+        for sg in fd.segs:
+            q = int(sg["query_seq"])
+            for c in fd.cands[int(sg["cand_begin"]):int(sg["cand_begin"]) + int(sg["cand_count"])]:
+                f.write("%s\t%d\t%d\t%d\t%s\t%d\t%d\t%s\t0\t%d\t%d\n" % (
+                    d.q_names[q], c["qstart"], c["qstop"], fd.q_len[q], d.ref_names[int(c["ref_seq"])], c["rstart"], c["rstop"],
+                    repr(float(c["score"])), c["identities"], c["alnlen"]))
+
+
+def reference_cases():
+    """Edge cases that are also run through the REAL reference binary (tests/golden/make_golden_edge.py)."""
+    return [("past_ends_nt", ranges_past_ends(False, far=False)), ("past_ends_aa", ranges_past_ends(True, far=False)),
+            ("n_rich", n_rich(b"NNnnacgt")), ("many_candidates", many_candidates())]

@@ -58,3 +58,13 @@ def test_many_candidates_one_segment(ctx):
 def test_stable_sort_with_ties(ctx):
     """SortFilter runs on the device (rank sort with the record position as tie-break)."""
     check(ctx, edge_data.score_ties())
+
+
+@pytest.mark.parametrize("name", ["past_ends_nt", "past_ends_aa", "n_rich", "many_candidates"])
+def test_edge_cases_against_the_real_reference(ctx, name):
+    """GPU == GFF3 of the real reference on the edge cases it can run (tests/golden/edge_*.gff3)."""
+    import golden_util as gu
+    fd = dict(edge_data.reference_cases())[name]
+    load(ctx, fd)
+    got = ctx.predict_batch(fd.segs, fd.cands)
+    assert gu.render_sorted(fd, got) == open(gu.os.path.join(gu.GOLDEN, "edge_%s.gff3" % name)).readlines()

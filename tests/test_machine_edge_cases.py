@@ -39,3 +39,17 @@ def test_many_candidates_one_segment():
 
 def test_stable_sort_with_ties():
     check(edge_data.score_ties())
+
+
+@pytest.mark.parametrize("name", ["past_ends_nt", "past_ends_aa", "n_rich", "many_candidates"])
+def test_edge_cases_against_the_real_reference(name):
+    """The edge cases the real reference can run (tests/golden/edge_*.gff3 from oracle/_ref/taxator,
+    make_golden_edge.py): reference ranges clipped at the sequence ends, N-rich sequences, 300-record sets --
+    oracle and host-compiled state machine reproduce its GFF3."""
+    import golden_util as gu
+    fd = dict(edge_data.reference_cases())[name]
+    want = open(gu.os.path.join(gu.GOLDEN, "edge_%s.gff3" % name)).readlines()
+    res = ol.oracle_predict(fd)
+    assert gu.render_sorted(fd, res) == want
+    got, _ = ol.host_machine_predict(fd)
+    assert ol.results_equal(res, got) == []

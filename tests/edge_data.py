@@ -101,6 +101,9 @@ def write_files_from_flat(fd, outdir):
                     repr(float(c["score"])), c["identities"], c["alnlen"]))
 
 
+PARAM_SETS = [("0.0", "0.05"), ("0.9", "0.05"), ("0.5", "0.3"), ("0.5", "0.0")]   # (-x, -t) as the command line spells them
+
+
 def reference_cases():
     """Edge cases that are also run through the REAL reference binary (tests/golden/make_golden_edge.py)."""
     return [("past_ends_nt", ranges_past_ends(False, far=False)), ("past_ends_aa", ranges_past_ends(True, far=False)),

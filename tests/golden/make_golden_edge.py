@@ -17,12 +17,15 @@ import edge_data  # noqa: E402
 
 def main():
     binary = os.path.join(ROOT, "oracle", "_ref", "taxator")
-    for name, fd in edge_data.reference_cases():
+    cases = [(name, fd, "0.5", "0.05") for name, fd in edge_data.reference_cases()]
+    # the two parameters of the model: -x (exclude_alignments_factor) and -t (re-evaluation band), hh:329-339
+    cases += [("params_x%s_t%s" % (x, t), edge_data.base(seed=24), x, t) for x, t in edge_data.PARAM_SETS]
+    for name, fd, x, t in cases:
         with tempfile.TemporaryDirectory() as tmp:
             edge_data.write_files_from_flat(fd, tmp)
             env = dict(os.environ, TAXATORTK_TAXONOMY_NCBI=tmp)
             cmd = [binary, "-a", "rpa", "-g", "mapping.tax", "-q", "query.fna", "-f", "ref.fna", "-i", "ref.fna.fai", "-p", "4",
-                   "-x", "0.5", "-o", "0"]
+                   "-x", x, "-t", t, "-o", "0"]
             if fd.protein:
                 cmd += ["-b", "protein"]
             with open(os.path.join(tmp, "alignments.tsv"), "rb") as fin:

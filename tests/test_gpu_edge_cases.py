@@ -68,3 +68,16 @@ def test_edge_cases_against_the_real_reference(ctx, name):
     load(ctx, fd)
     got = ctx.predict_batch(fd.segs, fd.cands)
     assert gu.render_sorted(fd, got) == open(gu.os.path.join(gu.GOLDEN, "edge_%s.gff3" % name)).readlines()
+
+
+@pytest.mark.parametrize("x,t", edge_data.PARAM_SETS)
+def test_parameters_against_the_real_reference(ctx, x, t):
+    import golden_util as gu
+    fd = edge_data.base(seed=24)
+    load(ctx, fd)
+    try:
+        ctx.set_params(float(x), float(t))
+        got = ctx.predict_batch(fd.segs, fd.cands)
+    finally:
+        ctx.set_params(0.5, 0.05)
+    assert gu.render_sorted(fd, got) == open(gu.os.path.join(gu.GOLDEN, "edge_params_x%s_t%s.gff3" % (x, t))).readlines()

@@ -53,3 +53,15 @@ def test_edge_cases_against_the_real_reference(name):
     assert gu.render_sorted(fd, res) == want
     got, _ = ol.host_machine_predict(fd)
     assert ol.results_equal(res, got) == []
+
+
+@pytest.mark.parametrize("x,t", edge_data.PARAM_SETS)
+def test_parameters_against_the_real_reference(x, t):
+    """-x / -t of the real reference (tests/golden/edge_params_*.gff3)."""
+    import golden_util as gu
+    fd = edge_data.base(seed=24)
+    want = open(gu.os.path.join(gu.GOLDEN, "edge_params_x%s_t%s.gff3" % (x, t))).readlines()
+    res = ol.oracle_predict(fd, exclude_factor=float(x), toppercent=float(t))
+    assert gu.render_sorted(fd, res) == want
+    got, _ = ol.host_machine_predict(fd, exclude_factor=float(x), toppercent=float(t))
+    assert ol.results_equal(res, got) == []

@@ -32,5 +32,26 @@ def main():
                 print(case, variant, len(lines), "lines,", sum("tax=1:" in l or "tax=1;" in l for l in lines), "at the root")
 
 
+def distinct():
+    """-c >= 2 on the input whose records have pairwise distinct query ranges (golden_util.LCA_C_VARIANTS)."""
+    binary = os.path.join(ROOT, "oracle", "_ref", "taxator")
+    d, evalue, named = gu.lca_distinct_case_data()
+    with tempfile.TemporaryDirectory() as tmp:
+        gu.lca_write_files(d, evalue, named, tmp)
+        env = dict(os.environ, TAXATORTK_TAXONOMY_NCBI=tmp)
+        for variant, (args, _) in gu.LCA_C_VARIANTS.items():
+            outs = []
+            for threads in ("1", "3"):     # the result must not depend on the allocator / thread interleaving here
+                with open(os.path.join(tmp, "alignments.tsv"), "rb") as fin:
+                    out = subprocess.run([binary] + args + ["-g", "mapping.tax", "-p", threads, "-o", "0"], cwd=tmp, env=env, stdin=fin,
+                                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout.decode()
+                outs.append(sorted(l + "\n" for l in out.splitlines() if not l.startswith("##")))
+            assert outs[0] == outs[1]
+            with open(os.path.join(HERE, "lca_distinct_%s.gff3" % variant), "w") as f:
+                f.writelines(outs[0])
+            print("distinct", variant, len(outs[0]), "lines,", sum("tax=1:" in l or "tax=1;" in l for l in outs[0]), "at the root")
+
+
 if __name__ == "__main__":
     main()
+    distinct()

@@ -91,6 +91,35 @@ LCA_VARIANTS = {
 }
 
 
+# megan-lca with -c >= 2: the support filter counts rises of the running maximum in record-set ORDER, and the reference
+# orders records of equal (qstart, qstop) by heap address (alignmentrecord.hh:479).  On inputs whose records have
+# DISTINCT query ranges inside a query the order is (qstart, qstop) for both sides, so -c >= 2 can be pinned there.
+LCA_DISTINCT_CASE = "nt_small"
+LCA_C_VARIANTS = {
+    "megan_c2": (["-a", "megan-lca", "-c", "2"], dict(model=2, toppercent=0.05, minscore=0.0, maxevalue=1000.0, minsupport=2)),
+    "megan_c3_t50": (["-a", "megan-lca", "-c", "3", "-t", "0.5"], dict(model=2, toppercent=0.5, minscore=0.0, maxevalue=1000.0, minsupport=3)),
+    "megan_c4_t100_u": (["-a", "ic-megan-lca", "-c", "4", "-t", "1.0", "-u"],
+                        dict(model=2, toppercent=1.0, minscore=0.0, maxevalue=1000.0, minsupport=4, ignore_unclassified=True)),
+}
+
+
+def lca_distinct_case_data():
+    """lca_case_data(LCA_DISTINCT_CASE) with the query ranges of a query's records made pairwise distinct (qstop
+    shortened by the record's rank among those that share its range)."""
+    import numpy as np
+    d, evalue, named = lca_case_data(LCA_DISTINCT_CASE)
+    r = d.rec
+    seen = {}
+    for k in range(len(r["q"])):
+        key = (int(r["q"][k]), int(r["qstart"][k]), int(r["qstop"][k]))
+        while key in seen and key[2] > key[1]:
+            key = (key[0], key[1], key[2] - 1)
+        assert key not in seen
+        seen[key] = k
+        r["qstop"][k] = key[2]
+    return d, evalue, named
+
+
 def lca_masked(d):
     """records masked in the input ('*' prefix, AlignmentRecord::isFiltered): every 17th line and ALL lines of
     the fourth query (a record set without any active record)"""

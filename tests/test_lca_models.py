@@ -38,6 +38,35 @@ def test_oracle_matches_reference_gff3(case):
         assert _render(d, tax[0], tax[3], segs, res) == gu.lca_golden_lines(case, variant), variant
 
 
+def _distinct_case():
+    d, evalue, named = gu.lca_distinct_case_data()
+    parent, left, right, depth = d.nested_set()
+    segs, cands, ev = gu.lca_flat(d, evalue)
+    return d, (parent, left, right, depth), segs, cands, ev, gu.lca_unclassified_flags(d, named)
+
+
+def _distinct_golden(variant):
+    return open(os.path.join(gu.GOLDEN, "lca_distinct_%s.gff3" % variant)).readlines()
+
+
+def test_oracle_matches_reference_with_min_support():
+    """megan-lca -c 2 / 3 / 4 pinned against the real binary on records with pairwise distinct query ranges (where the
+    reference's record order does not depend on heap addresses)."""
+    d, tax, segs, cands, ev, uncl = _distinct_case()
+    for variant, (_, kw) in gu.LCA_C_VARIANTS.items():
+        res = ol.oracle_predict_lca(*tax, segs, cands, ev, uncl, **kw)
+        assert _render(d, tax[0], tax[3], segs, res) == _distinct_golden(variant), variant
+
+
+@pytest.mark.gpu
+def test_gpu_matches_reference_with_min_support(ctx):
+    d, tax, segs, cands, ev, uncl = _distinct_case()
+    ctx.load_taxonomy(*tax, 0)
+    for variant, (_, kw) in gu.LCA_C_VARIANTS.items():
+        got, _ = ctx.predict_lca_batch(kw["model"], segs, cands, ev, uncl, **{k: v for k, v in kw.items() if k != "model"})
+        assert _render(d, tax[0], tax[3], segs, got) == _distinct_golden(variant), variant
+
+
 def _random_tables(rng, n_nodes, n_segs):
     """Adversarial record sets: ties, reversed query ranges, empty and > 32-record sets, scores below / above 0."""
     counts = rng.choice([0, 1, 2, 3, 7, 31, 32, 33, 64, 65, 150], n_segs)

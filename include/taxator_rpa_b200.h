@@ -142,7 +142,7 @@ int trpa_set_band(trpa_ctx* ctx, int on);
  * where the kernel's certificate proves that exact), "plan_lanes" = weight of a pair's latency in the shape
  * planner (0: the resident lanes), "tail_log2" = its convex term time^2 / 2^tail_log2, "hint_mul64" /
  * "hint_add" = safety margin on distance estimates, "cost_word10" / "cost_col10" / "cost_step" / "cost_setup" /
- * "cost_setup_w" = the planner's instruction-cost model, "la_cap" / "la_max" = look-ahead budget per round /
+ * "cost_setup_w" = the planner's instruction-cost model, "la_cap" (0 = scaled with the batch) / "la_max" = look-ahead budget per round /
  * per segment, "force_shape" = one kernel shape for every pair. */
 int trpa_set_tuning(trpa_ctx* ctx, const char* key, int64_t value);
 int trpa_profile_reset(trpa_ctx* ctx);

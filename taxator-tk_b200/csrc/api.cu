@@ -181,7 +181,9 @@ struct trpa_ctx {
   Pipe pipe[kMaxPipes];
   int n_pipes = 1;   // measured on C2: overlapping chunks gains nothing (the alignment kernels already saturate the GPU)
   u32 band_k0 = 0;            // test hook: forced initial threshold (0 = planned), exercises the retry loop
-  u32 la_cap = 300000;        // pairs per round the automatic look-ahead aims for (measured: C2 +10 %, C1 2.4x vs none)
+  u32 la_cap = 0;             // pairs per round the automatic look-ahead aims for; 0 = scaled with the chunk: 5.5 per
+                              // segment within [150 k, 750 k] (measured, DESIGN.md section 6: C2 prefers 550 k for 100 k
+                              // segments, the 250 k-segment C4 shard 750 k, the 50 k-segment protein batch 150-300 k)
   u32 la_max = 32;            // largest automatic look-ahead budget per segment and round
   int force_shape = -1;       // tuning hook: (lidx * kNumW + widx) forced for every pair, -1 = planner
   PlanParams plan;            // hint margin + cost model of the shape planner (tuning hooks)
@@ -529,7 +531,7 @@ int trpa_set_tuning(trpa_ctx* c, const char* key, int64_t value) {
   else if (k == "wedge_cushion") c->plan.wedge_cushion = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 16));
   else if (k == "plan_lanes") c->plan_lanes = value < 0 ? 0u : (u32)std::min<int64_t>(value, 1 << 30);
   else if (k == "wedge") c->wedge = value < 0 ? 0 : (value > 2 ? 2 : (int)value);   // 2: test hook, see plan_kernel
-  else if (k == "la_cap") c->la_cap = (u32)std::max<int64_t>(1, value);
+  else if (k == "la_cap") c->la_cap = (u32)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
   else if (k == "la_max") c->la_max = (u32)std::max<int64_t>(0, std::min<int64_t>(64, value));
   else if (k == "force_shape") c->force_shape = value < 0 || value >= kNumW * kNumL ? -1 : (int)value;
   else if (k == "pipes") c->n_pipes = (int)std::max<int64_t>(1, std::min<int64_t>(trpa_ctx::kMaxPipes, value));
@@ -898,7 +900,9 @@ static int step_pipe(trpa_ctx* c, Pipe& P, int pipe_index, size_t& next_chunk, c
     // (a banded pair needs only a few lanes; more pairs per round = cheaper shapes, fewer dependent rounds)
     if (c->lookahead >= 0) P.B.spec_k = (u32)c->lookahead;
     else {
-      const u32 cap = c->la_cap / (u32)c->run_pipes;
+      const u32 chunk_segs = P.se - P.sb;
+      const u32 cap_auto = (u32)std::min<u64>(750000u, std::max<u64>(150000u, (u64)chunk_segs * 11u / 2u));
+      const u32 cap = c->la_cap ? c->la_cap / (u32)c->run_pipes : cap_auto;
       P.B.spec_k = n_active ? std::min<u32>(c->la_max, cap / n_active > 0 ? cap / n_active - 1 : 0) : 0;
     }
     if (P.h_counters[CN_OVERFLOW]) { set_error("internal: staging arena overflow"); return TRPA_ERR_STATE; }

@@ -147,6 +147,7 @@ struct trpa_ctx {
   int run_pipes = 1;             // pipes the uploaded batch was planned for
   u32 n_segs = 0, n_cands = 0;
   u32 max_stage_len = 0;
+  u32 avg_stage_len = 0;         // average length of the segments the batch can stage (look-ahead budget)
   bool batch_ready = false;
   DevBuf<trpa_segment> d_segs;
   DevBuf<trpa_candidate> d_cands;      // SortFilter order
@@ -806,6 +807,7 @@ int trpa_batch_upload(trpa_ctx* c, const trpa_segment* segs, uint32_t n_segs, co
   // extensions can add at most the query range; sequences are clipped to the store anyway
   max_len = std::min<u64>((u64)max_len + Q.max_len, std::max(R.max_len, Q.max_len));
   c->max_stage_len = max_len;
+  c->avg_stage_len = (u32)std::min<u64>(0xffffffffull, (protein ? total_bound : total_bound * 32ull) / std::max<u64>(1, (u64)n_cands + n_segs));
   // chunks of segments: every pipe works on one chunk at a time inside its own arena region
   const int K = (c->n_pipes > 1 && n_segs >= 8192u) ? c->n_pipes : 1;
   u64 cap_pipe = units_cap / K;
@@ -901,7 +903,11 @@ static int step_pipe(trpa_ctx* c, Pipe& P, int pipe_index, size_t& next_chunk, c
     if (c->lookahead >= 0) P.B.spec_k = (u32)c->lookahead;
     else {
       const u32 chunk_segs = P.se - P.sb;
-      const u32 cap_auto = (u32)std::min<u64>(750000u, std::max<u64>(150000u, (u64)chunk_segs * 11u / 2u));
+      // long pairs fill the GPU with fewer of them and a wasted look-ahead alignment costs more: beyond 12 kb average
+      // the budget shrinks in proportion (200 k x 10-50 kb reads: 750 k pairs per round cost 3.5 %)
+      u64 cap_scaled = std::min<u64>(750000u, std::max<u64>(150000u, (u64)chunk_segs * 11u / 2u));
+      if (c->avg_stage_len > 12000u) cap_scaled = std::max<u64>(150000u, cap_scaled * 12000u / c->avg_stage_len);
+      const u32 cap_auto = (u32)cap_scaled;
       const u32 cap = c->la_cap ? c->la_cap / (u32)c->run_pipes : cap_auto;
       P.B.spec_k = n_active ? std::min<u32>(c->la_max, cap / n_active > 0 ? cap / n_active - 1 : 0) : 0;
     }

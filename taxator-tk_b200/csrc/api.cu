@@ -87,8 +87,9 @@ struct Store {
   DevBuf<u64> woff;
   DevBuf<u32> len;
   u32 max_len = 0;
+  u32 aa_mask = 0;          // AA: residue ordinals that occur in the store (profile rows of the protein kernel)
   std::vector<u32> h_len;   // host copy of the sequence lengths (upload validation)
-  void release() { planes.release(); nplane.release(); packed.release(); woff.release(); len.release(); n_seq = 0; alphabet = -1; h_len.clear(); }
+  void release() { planes.release(); nplane.release(); packed.release(); woff.release(); len.release(); n_seq = 0; alphabet = -1; aa_mask = 0; h_len.clear(); }
 };
 
 struct EventPair { cudaEvent_t a, b; int kind; };
@@ -563,6 +564,19 @@ int trpa_load_taxonomy(trpa_ctx* c, const uint32_t* parent, const uint32_t* left
   return 0;
 }
 
+// residue ordinals present in a packed AA store (one pass at load time)
+static int aa_store_mask(trpa_ctx* c, Store& S, u64 n_words) {
+  ScopedBuf<u32> d_mask;
+  if (d_mask.ensure(1)) return TRPA_ERR_NOMEM;
+  CK(cudaMemsetAsync(d_mask.p, 0, sizeof(u32), c->stream));
+  CK(launch_aa_mask(S.packed.p, n_words, d_mask.p, c->stream));
+  u32 h = 0;
+  CK(cudaMemcpyAsync(&h, d_mask.p, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  S.aa_mask = (h | 1u) & 0x7ffffffu;
+  return 0;
+}
+
 int trpa_load_store(trpa_ctx* c, int store, int alphabet, const char* chars, const uint64_t* off, const uint32_t* len,
                     uint32_t n_seq) {
   if (!c || store < 0 || store > 1 || (alphabet != TRPA_ALPHA_NT && alphabet != TRPA_ALPHA_AA) || (n_seq && (!chars || !off || !len))) {
@@ -607,6 +621,8 @@ int trpa_load_store(trpa_ctx* c, int store, int alphabet, const char* chars, con
     CK(cudaMemsetAsync(S.packed.p, 0, (words + 2) * sizeof(u32), c->stream));
     CK(launch_pack_aa(d_chars.p, d_off.p, S.woff.p, S.len.p, n_seq, words, S.packed.p, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    const int rc = aa_store_mask(c, S, words);
+    if (rc) return rc;
   }
   d_chars.release(); d_off.release();
   S.alphabet = alphabet; S.n_seq = n_seq; S.n_words = words; S.max_len = maxlen;
@@ -678,6 +694,8 @@ int trpa_load_store_packed(trpa_ctx* c, int store, int alphabet, const uint64_t*
     if (S.packed.ensure(n_words + 2)) return TRPA_ERR_NOMEM;
     CK(cudaMemsetAsync(S.packed.p + n_words, 0, 2 * sizeof(u32), c->stream));
     if (n_words) CK(cudaMemcpyAsync(S.packed.p, in, 4ull * n_words, cudaMemcpyHostToDevice, c->stream));
+    const int rc = aa_store_mask(c, S, n_words);
+    if (rc) return rc;
   }
   CK(cudaStreamSynchronize(c->stream));
   S.alphabet = alphabet; S.n_seq = n_seq; S.n_words = n_words; S.max_len = maxlen;
@@ -948,7 +966,7 @@ static int step_pipe(trpa_ctx* c, Pipe& P, int pipe_index, size_t& next_chunk, c
       }
       ev = begin_event(P, EV_PROTEIN);
       CK(launch_protein(P.pairs, n_pairs, c->d_descs.p, c->arena_aa.p, (int2*)c->d_res.p, scr, stride,
-                        c->max_stage_len, P.stream));
+                        c->max_stage_len, c->store[0].aa_mask | c->store[1].aa_mask, P.stream));
       end_event(P, ev);
       c->prof.launches_protein++;
       CK(cudaMemsetAsync(P.d_counters.p + CN_PAIRS, 0, sizeof(u32) * 3, P.stream));
@@ -1245,9 +1263,9 @@ int trpa_protein_align_batch(trpa_ctx* c, const char* chars, const uint64_t* off
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   if (repeat < 1) repeat = 1;
-  if (kernel_ms && repeat > 1) CK(launch_protein(d_pairs.p, n_pairs, d_sd.p, d_codes.p, d_out.p, scr, stride, max_len, c->stream));
+  if (kernel_ms && repeat > 1) CK(launch_protein(d_pairs.p, n_pairs, d_sd.p, d_codes.p, d_out.p, scr, stride, max_len, 0u, c->stream));
   CK(cudaEventRecord(e0, c->stream));
-  for (int r = 0; r < repeat; ++r) CK(launch_protein(d_pairs.p, n_pairs, d_sd.p, d_codes.p, d_out.p, scr, stride, max_len, c->stream));
+  for (int r = 0; r < repeat; ++r) CK(launch_protein(d_pairs.p, n_pairs, d_sd.p, d_codes.p, d_out.p, scr, stride, max_len, 0u, c->stream));
   CK(cudaEventRecord(e1, c->stream));
   std::vector<int2> ho(n_pairs);
   CK(cudaMemcpyAsync(ho.data(), d_out.p, sizeof(int2) * n_pairs, cudaMemcpyDeviceToHost, c->stream));

@@ -37,8 +37,10 @@ cudaError_t launch_binner(const trpa_bin_record* recs, u32 n_records, const u32*
 
 // BLOSUM62 linear-gap NW with traced length; out2[pair.out] = {mutual, #diagonal steps}
 // scratch: scratch_stride int2 per pair, needed only when a pair's A is longer than 512 residues
+// aa_mask: bit r set = residue ordinal r may occur in the staged sequences (0 = unknown: all 27); the short-pair kernel
+// keeps profile rows only for those residues (more resident pairs per SM) and traps on a residue outside the mask
 cudaError_t launch_protein(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,
-                           int2* out2, int2* scratch, u32 scratch_stride, u32 max_len, cudaStream_t stream);
+                           int2* out2, int2* scratch, u32 scratch_stride, u32 max_len, u32 aa_mask, cudaStream_t stream);
 
 // ASCII -> packed stores
 cudaError_t launch_pack_nt(const uint8_t* chars, const u64* off, const SeqDesc* seqs, u32 n_seq, u64 total_words,
@@ -46,6 +48,7 @@ cudaError_t launch_pack_nt(const uint8_t* chars, const u64* off, const SeqDesc* 
 
 cudaError_t ensure_blosum_constant(int device);
 cudaError_t launch_aa_codes(const uint8_t* chars, uint8_t* out, u64 n, cudaStream_t stream);
+cudaError_t launch_aa_mask(const u32* packed, u64 n_words, u32* mask, cudaStream_t stream);
 cudaError_t launch_pack_aa(const uint8_t* chars, const u64* off, const u64* woff, const u32* len, u32 n_seq,
                            u64 total_words, u32* packed, cudaStream_t stream);
 cudaError_t launch_stage_nt(const StageReq* reqs, u32 n_req, const uint2* q_planes, const u32* q_n, const u64* q_woff,

@@ -138,6 +138,28 @@ __global__ void pack_aa_kernel(const uint8_t* __restrict__ chars, const u64* __r
   }
 }
 
+// which of the 27 residue ordinals occur in a packed store (bit r of *mask; unused fields of a sequence's last word
+// read as ordinal 0) -- sizes the query profile of the protein kernel
+__global__ void aa_mask_kernel(const u32* __restrict__ packed, u64 n_words, u32* __restrict__ mask) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  u32 m = 0;
+  for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+    const u32 x = packed[w];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) m |= 1u << ((x >> (5 * k)) & 31u);
+  }
+  m = __reduce_or_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicOr(mask, m);
+}
+
+cudaError_t launch_aa_mask(const u32* packed, u64 n_words, u32* mask, cudaStream_t stream) {
+  if (n_words == 0) return cudaSuccess;
+  u64 blocks = (n_words + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  aa_mask_kernel<<<(u32)blocks, 256, 0, stream>>>(packed, n_words, mask);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_pack_aa(const uint8_t* chars, const u64* off, const u64* woff, const u32* len, u32 n_seq,
                            u64 total_words, u32* packed, cudaStream_t stream) {
   if (total_words == 0) return cudaSuccess;

@@ -120,17 +120,17 @@ protein_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __r
 }
 
 cudaError_t launch_protein2(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,
-                            int2* out2, int2* scratch, u32 scratch_stride, u32 max_len, cudaStream_t stream);
+                            int2* out2, int2* scratch, u32 scratch_stride, u32 max_len, u32 aa_mask, cudaStream_t stream);
 int protein2_max_len();
 
 // max_len: longest staged sequence of the launch (decides whether the 32-bit fallback kernel runs)
 cudaError_t launch_protein(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,
-                           int2* out2, int2* scratch, u32 scratch_stride, u32 max_len, cudaStream_t stream) {
+                           int2* out2, int2* scratch, u32 scratch_stride, u32 max_len, u32 aa_mask, cudaStream_t stream) {
   if (count == 0) return cudaSuccess;
   cudaError_t e = ensure_table();
   if (e != cudaSuccess) return e;
   const u32 blocks = (count + 3) / 4;
-  e = launch_protein2(pairs, count, seqs, residues, out2, scratch, scratch_stride, max_len, stream);
+  e = launch_protein2(pairs, count, seqs, residues, out2, scratch, scratch_stride, max_len, aa_mask, stream);
   if (e != cudaSuccess) return e;
   if ((int)max_len > protein2_max_len()) {
     protein_kernel<<<blocks, 128, 0, stream>>>(pairs, count, seqs, residues, out2, scratch, scratch_stride, protein2_max_len());

@@ -325,6 +325,15 @@ static bool protein_half_enabled() {
   if (v < 0) { const char* e = getenv("TRPA_PROTEIN_HALF"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
+// protein3.cu: eight lanes per pair, the default for the pairs the half-warp kernel would take (A/B hook:
+// TRPA_PROTEIN_QUARTER=0 runs the half-warp kernel instead)
+cudaError_t launch_protein3(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues, int2* out2,
+                            u32 max_len, u32 aa_mask, cudaStream_t stream);
+static bool protein_quarter_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TRPA_PROTEIN_QUARTER"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 
 static cudaError_t launch_h(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues, int2* out2,
                             cudaStream_t stream) {
@@ -342,7 +351,7 @@ static cudaError_t launch_h(const PairDesc* pairs, u32 count, const SeqDesc* seq
 }
 
 cudaError_t launch_protein2(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,
-                            int2* out2, int2* scratch, u32 scratch_stride, u32 max_len, cudaStream_t stream) {
+                            int2* out2, int2* scratch, u32 scratch_stride, u32 max_len, u32 aa_mask, cudaStream_t stream) {
   if (count == 0) return cudaSuccess;
   cudaError_t e = ensure_table2();
   if (e != cudaSuccess) return e;
@@ -353,7 +362,11 @@ cudaError_t launch_protein2(const PairDesc* pairs, u32 count, const SeqDesc* seq
     attr = true;
   }
   const bool half = protein_half_enabled();
-  if (half) { e = launch_h(pairs, count, seqs, residues, out2, stream); if (e != cudaSuccess) return e; }
+  if (half) {
+    e = protein_quarter_enabled() ? launch_protein3(pairs, count, seqs, residues, out2, max_len, aa_mask, stream)
+                                  : launch_h(pairs, count, seqs, residues, out2, stream);
+    if (e != cudaSuccess) return e;
+  }
   const u32 blocks = (count + kP2Warps - 1) / kP2Warps;
   // profile capacity: columns per lane of the longest strip any pair of this launch can have
   const u32 longest = max_len ? (max_len > (u32)kP2MaxLen ? (u32)kP2MaxLen : max_len) : (u32)kP2MaxLen;

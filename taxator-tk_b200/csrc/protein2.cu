@@ -338,7 +338,10 @@ static bool protein_quarter_enabled() {
 static cudaError_t launch_h(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues, int2* out2,
                             cudaStream_t stream) {
   const size_t smem = (size_t)kP2Warps * 27 * kHCQ * 128 + 27 * 32;
-  static bool attr = false;
+  static bool attr_set[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& attr = attr_set[dev & 15];   // function attributes are per device
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(protein2h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -355,7 +358,10 @@ cudaError_t launch_protein2(const PairDesc* pairs, u32 count, const SeqDesc* seq
   if (count == 0) return cudaSuccess;
   cudaError_t e = ensure_table2();
   if (e != cudaSuccess) return e;
-  static bool attr = false;
+  static bool attr_set[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& attr = attr_set[dev & 15];   // function attributes are per device
   if (!attr) {
     e = cudaFuncSetAttribute(protein2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kP2SmemBytes);
     if (e != cudaSuccess) return e;

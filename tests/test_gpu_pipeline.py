@@ -37,6 +37,25 @@ def test_pipeline_matches_oracle(ctx, case):
     assert ol.results_equal(want, got) == []
 
 
+def test_protein_full_alphabet(ctx):
+    """All 27 SeqAn AminoAcid letters (and lower case / unknown characters) in both stores: the short-pair protein
+    kernel keeps one profile row per residue the stores contain (here all of them)."""
+    d = synth.generate(synth.SynthConfig(**CASES[2]))
+    rng = np.random.default_rng(99)
+    full = np.frombuffer(b"ABCDEFGHIJKLMNOPQRSTUVWYZX*acdxz-", np.uint8)
+    for seqs in (d.ref_seqs, d.q_seqs):
+        for k in range(len(seqs)):
+            s_ = seqs[k].copy()
+            hit = rng.random(len(s_)) < 0.03
+            s_[hit] = full[rng.integers(0, len(full), int(hit.sum()))]
+            seqs[k] = np.ascontiguousarray(s_)
+    fd = ol.FlatData(d)
+    want = ol.oracle_predict(fd)
+    load(ctx, fd)
+    got = ctx.predict_batch(fd.segs, fd.cands)
+    assert ol.results_equal(want, got) == []
+
+
 def test_small_arena_chunks(ctx):
     case = CASES[0]
     fd = ol.FlatData(synth.generate(synth.SynthConfig(**case)))

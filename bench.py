@@ -785,10 +785,13 @@ def main():
     # ---- roofline of the dominant kernel
     if fd.protein:
         k_ms, k_launch = prof["ms_protein"], prof["launches_protein"]
-        # protein2_kernel issues 3 alu-pipe instructions per DP cell (2 VIADDMNMX + 1 LOP3; the
-        # multiply-add of the diagonal runs on the fma pipe, the profile lookup on the LSU)
-        peak = alu_peak / 3.0 / 1e9
-        kname = "protein2_kernel"
+        # protein3_kernel issues 3 alu-pipe instructions per DP cell in two of three columns (2 VIADDMNMX + 1 LOP3; the
+        # multiply-add of the diagonal runs on the fma pipe, the profile lookup on the LSU) and 2 in every third column
+        # (both additions as IMAD on the fma pipe + VIMNMX3 + LOP3): 8/3 per cell -- the mix at which the alu pipe and the
+        # issue slots (16/3 per cell) bound the kernel at the same rate.  Round 1 quoted 3 per cell: frac_r01_constant.
+        ALU_OPS_PER_CELL_AA = 8.0 / 3.0
+        peak = alu_peak / ALU_OPS_PER_CELL_AA / 1e9
+        kname = "protein3_kernel"
     else:
         k_ms, k_launch = prof["ms_edit_distance"], prof["launches_edit_distance"]
         peak = alu_peak * 32.0 / ALU_OPS_PER_WORDSTEP / 1e9
@@ -811,11 +814,13 @@ def main():
                 "executed_cell_fraction": executed_cells / (cells_step * args.steps) if cells_step else None,
                 "band": bool(args.band) and not fd.protein, "band_retries_per_step": prof["band_retries"] / args.steps,
                 "peak_source": "own probe trpa_int_alu_peak (%.3e lane-ops/s) / %.1f ALU ops per 32-cell word-step"
-                               % (alu_peak, ALU_OPS_PER_WORDSTEP) if not fd.protein else "own probe trpa_int_alu_peak / 3 alu ops per cell",
-                "peak_lane_ops": alu_peak, "alu_ops_per_unit": 3.0 if fd.protein else ALU_OPS_PER_WORDSTEP,
+                               % (alu_peak, ALU_OPS_PER_WORDSTEP) if not fd.protein else "own probe trpa_int_alu_peak / (8/3) alu ops per cell",
+                "peak_lane_ops": alu_peak, "alu_ops_per_unit": ALU_OPS_PER_CELL_AA if fd.protein else ALU_OPS_PER_WORDSTEP,
                 "executed_cells_note": "executed cells = 32x32-cell word-blocks the kernel walked: a pair's partial last text block "
                                        "counts as 32 columns, and blocks of re-run attempts (band_retries) are included",
                 "kernel_ms_per_step": k_ms / args.steps, "kernel_share_of_step": (k_ms / args.steps) / ms_step}
+    if fd.protein and peak:
+        roofline["frac_r01_constant"] = roofline["frac"] * ALU_OPS_PER_CELL_AA / 3.0   # against lane-ops/s / 3 (round 1)
     if not fd.protein and peak:
         roofline["frac_r01_constant"] = roofline["frac"] * ALU_OPS_PER_WORDSTEP_R01 / ALU_OPS_PER_WORDSTEP
         # Round 2 narrows the wedge further (fewer executed cells for the same integers), which LOWERS `frac` (per-step

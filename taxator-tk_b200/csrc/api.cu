@@ -923,7 +923,9 @@ static int step_pipe(trpa_ctx* c, Pipe& P, int pipe_index, size_t& next_chunk, c
       const u32 chunk_segs = P.se - P.sb;
       // long pairs fill the GPU with fewer of them and a wasted look-ahead alignment costs more: beyond 12 kb average
       // the budget shrinks in proportion (200 k x 10-50 kb reads: 750 k pairs per round cost 3.5 %)
-      u64 cap_scaled = std::min<u64>(750000u, std::max<u64>(150000u, (u64)chunk_segs * 11u / 2u));
+      // (protein: every alignment is a full matrix, an unused look-ahead result costs as much as a used one: 3 pairs
+      // per segment, measured on C3 with 150 k against 275 k pairs per round: +0.9 %, gpurun_out/r2_35)
+      u64 cap_scaled = std::min<u64>(750000u, std::max<u64>(150000u, protein ? (u64)chunk_segs * 3u : (u64)chunk_segs * 11u / 2u));
       if (c->avg_stage_len > 12000u) cap_scaled = std::max<u64>(150000u, cap_scaled * 12000u / c->avg_stage_len);
       const u32 cap_auto = (u32)cap_scaled;
       const u32 cap = c->la_cap ? c->la_cap / (u32)c->run_pipes : cap_auto;

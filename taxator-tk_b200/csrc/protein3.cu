@@ -62,9 +62,9 @@ __device__ __forceinline__ void sts32(u32 addr, u32 v) { asm volatile("st.shared
 // One pair on the 8 lanes of a quarter warp, C columns per lane, RIGHT aligned (the first 8 * C - n columns of the low
 // lanes are padding: profile 0, row-0 value 0 -- the vertical candidate reproduces the left boundary column there, see
 // protein2.cu).  All four quarters of a warp run the same number of steps (the longest B of the four decides).
-template <int C, int R>
+template <int C, int R, int ALT>
 __device__ __forceinline__ void protein3_run(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n, int m,
-                                             bool mine, u32 prof_sa, u32 t2_sa, u32 lp, int steps, u32 mask,
+                                             bool mine, u32 prof_sa, u32 t2_sa, u32 lp, int steps, u32 mask, int one,
                                              int2* __restrict__ out2, u32 oidx) {
   constexpr int CQ = (C + 3) / 4;   // the profile keeps whole column quads; columns >= C of the last quad stay unused
   const int pad = kQLanes * C - n;                // leading padding columns
@@ -161,9 +161,19 @@ __device__ __forceinline__ void protein3_run(const uint8_t* __restrict__ a, cons
             int e;
             asm volatile("ld.shared.u8 %0, [%1];" : "=r"(e) : "r"(prow[r] + (u32)((c >> 2) * 128 + (c & 3))));
             const int D = e * (1 << (SH - 1)) + dg[r];   // score + sub, priority 2, gaps unchanged, row bias + 1
-            const int V = up[c] + CV;
-            const int H = left[r] + CH;
-            const int cell = max3i(D, V, H) & ~PRIO_MASK;
+            int cell;
+            if (ALT > 0 && c % ALT == ALT - 1) {
+              // every ALT-th column: both additions on the fma pipe (IMAD with a multiplier ptxas cannot fold) and one
+              // three-way maximum -- 2 instead of 3 alu-pipe instructions for this cell, one more issue slot
+              int V, H;
+              asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(V) : "r"(up[c]), "r"(one), "r"(CV));
+              asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(H) : "r"(left[r]), "r"(one), "r"(CH));
+              cell = __vimax3_s32(D, V, H) & ~PRIO_MASK;
+            } else {
+              const int V = up[c] + CV;
+              const int H = left[r] + CH;
+              cell = max3i(D, V, H) & ~PRIO_MASK;
+            }
             dg[r] = up[c];
             up[c] = cell;
             left[r] = cell;
@@ -188,10 +198,10 @@ __device__ __forceinline__ void protein3_run(const uint8_t* __restrict__ a, cons
   }
 }
 
-template <int R>
+template <int R, int ALT>
 __global__ void __launch_bounds__(32 * kQWarps, 1)
 protein3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __restrict__ seqs,
-                const uint8_t* __restrict__ residues, int2* __restrict__ out2, u32 cq_cap, u32 mask) {
+                const uint8_t* __restrict__ residues, int2* __restrict__ out2, u32 cq_cap, u32 mask, int one) {
   // cq_cap: column quads per lane the shared-memory profile is sized for (the launch's longest sequence decides);
   // mask: residue ordinals that may occur (one profile row each)
   extern __shared__ __align__(16) unsigned char smem3[];
@@ -227,18 +237,25 @@ protein3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __
   const int steps = (mmax + R - 1) / R + (kQLanes - 1);
   const u32 prof_sa = (u32)__cvta_generic_to_shared(prof_all) + (warp_in_cta * (u32)__popc(mask) * cq_cap * 32u + lane) * 4u;
   const u32 t2_sa = (u32)__cvta_generic_to_shared(t2);
-  if (cols <= 8) protein3_run<8, R>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, out2, oidx);
-  else if (cols <= 16) protein3_run<16, R>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, out2, oidx);
-  else if (cols <= 24) protein3_run<24, R>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, out2, oidx);
-  else if (cols <= 32) protein3_run<32, R>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, out2, oidx);
-  else if (cols <= 36) protein3_run<36, R>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, out2, oidx);
-  else if (cols <= 38) protein3_run<38, R>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, out2, oidx);
-  else protein3_run<40, R>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, out2, oidx);
+  if (cols <= 8) protein3_run<8, R, ALT>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, one, out2, oidx);
+  else if (cols <= 16) protein3_run<16, R, ALT>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, one, out2, oidx);
+  else if (cols <= 24) protein3_run<24, R, ALT>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, one, out2, oidx);
+  else if (cols <= 32) protein3_run<32, R, ALT>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, one, out2, oidx);
+  else if (cols <= 36) protein3_run<36, R, ALT>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, one, out2, oidx);
+  else if (cols <= 38) protein3_run<38, R, ALT>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, one, out2, oidx);
+  else protein3_run<40, R, ALT>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, one, out2, oidx);
 }
 
-int protein_rows_per_step() {
+// 0 (default): four rows per step, every 3rd column in the fma-heavy form; A/B hooks: TRPA_PROTEIN_ROWS=2 (1: two rows,
+// plain cells), TRPA_PROTEIN_ALT=4 / 0 / 2 (2 / 3 / 4: four rows with every 4th / no / every 2nd column fma-heavy).
+// Measured on C3 (gpurun_out/r2_34): plain 34.0 ms of alignment per step, every 4th 33.2, every 3rd 33.0.
+int protein3_variant() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("TRPA_PROTEIN_ROWS"); v = (e && e[0] == '2') ? 2 : 4; }
+  if (v < 0) {
+    v = 0;
+    if (const char* e = getenv("TRPA_PROTEIN_ROWS")) if (e[0] == '2') v = 1;
+    if (const char* e = getenv("TRPA_PROTEIN_ALT")) { if (e[0] == '4') v = 2; else if (e[0] == '0') v = 3; else if (e[0] == '2') v = 4; }
+  }
   return v;
 }
 
@@ -261,25 +278,25 @@ cudaError_t launch_protein3(const PairDesc* pairs, u32 count, const SeqDesc* seq
   const u32 cols = (longest + kQLanes - 1) / kQLanes;
   const u32 cq = cols <= 8 ? 2u : (cols <= 16 ? 4u : (cols <= 24 ? 6u : (cols <= 32 ? 8u : (cols <= 36 ? 9u : 10u))));
   const size_t smem = 1024 + (size_t)kQWarps * nrows * cq * 128;
-  const int R = protein_rows_per_step();
-  static bool attr_set[16][2] = {{false}};
+  typedef void (*Kern)(const PairDesc*, u32, const SeqDesc*, const uint8_t*, int2*, u32, u32, int);
+  static const Kern kerns[5] = {protein3_kernel<4, 3>, protein3_kernel<2, 0>, protein3_kernel<4, 4>, protein3_kernel<4, 0>, protein3_kernel<4, 2>};
+  const int variant = protein3_variant();
+  const Kern kern = kerns[variant];
+  static bool attr_set[16][5] = {{false}};
   int dev = 0;
   cudaGetDevice(&dev);
-  bool& attr = attr_set[dev & 15][R == 2 ? 0 : 1];   // the attributes are per device
+  bool& attr = attr_set[dev & 15][variant];   // the attributes are per device
   if (!attr) {
     const int cap = (int)(1024 + kQWarps * 27 * 10 * 128);
-    e = R == 2 ? cudaFuncSetAttribute(protein3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)
-               : cudaFuncSetAttribute(protein3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e != cudaSuccess) return e;
-    e = R == 2 ? cudaFuncSetAttribute(protein3_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
-               : cudaFuncSetAttribute(protein3_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
     attr = true;
   }
   const u32 warps = (count + 3u) / 4u;
   const u32 blocks = (warps + kQWarps - 1) / kQWarps;
-  if (R == 2) protein3_kernel<2><<<blocks, 32 * kQWarps, smem, stream>>>(pairs, count, seqs, residues, out2, cq, mask);
-  else protein3_kernel<4><<<blocks, 32 * kQWarps, smem, stream>>>(pairs, count, seqs, residues, out2, cq, mask);
+  kern<<<blocks, 32 * kQWarps, smem, stream>>>(pairs, count, seqs, residues, out2, cq, mask, 1);
   return cudaGetLastError();
 }
 

@@ -43,13 +43,21 @@ __global__ void plan_kernel(PairDesc* __restrict__ pairs, u32 n_pairs, const Seq
       u32* bins = plan_bins[threadIdx.x >> 5];
       bins[lane] = 0u;
       __syncwarp();
+      // (the words of the NEXT iteration are requested before this iteration's are used: the loop was the kernel's
+      // largest stall, 36 % of the samples on the first use of a word just loaded)
+      const uint2 zero2 = make_uint2(0u, 0u);
+      uint2 x = lane < mwords ? planes[pw + lane] : zero2, y = lane < mwords ? planes[tw + lane] : zero2;
+      u32 xn = (hasn && lane < mwords) ? nplane[pw + lane] : 0u, yn = (hasn && lane < mwords) ? nplane[tw + lane] : 0u;
       for (u32 w = lane; w < mwords; w += 32u) {
-        const uint2 x = planes[pw + w], y = planes[tw + w];
-        u32 mm = (x.x ^ y.x) | (x.y ^ y.y);
-        if (hasn) mm |= nplane[pw + w] ^ nplane[tw + w];
+        const u32 wn = w + 32u;
+        const bool more = wn < mwords;
+        const uint2 x2 = more ? planes[pw + wn] : zero2, y2 = more ? planes[tw + wn] : zero2;
+        const u32 xn2 = (hasn && more) ? nplane[pw + wn] : 0u, yn2 = (hasn && more) ? nplane[tw + wn] : 0u;
+        u32 mm = (x.x ^ y.x) | (x.y ^ y.y) | (xn ^ yn);
         if (w == mwords - 1 && (m & 31u)) mm &= (1u << (m & 31u)) - 1u;
         const u32 c = __popc(mm);
         if (c) atomicAdd(&bins[w / per], c);
+        x = x2; y = y2; xn = xn2; yn = yn2;
       }
       __syncwarp();
       const u32 h = bins[lane];

@@ -155,7 +155,8 @@ TRPA_HD uint64_t band_steps(const BandGeom& g, int W, int L) {
     uint64_t acc = 0;
     uint32_t n = 0;
     for (uint32_t r = 0; r < rounds; r += stride, ++n) acc += (uint64_t)L + (uint64_t)g.round_gap(r, (uint32_t)W, (uint32_t)L, S);
-    off = acc * rounds / n;
+    // (32-bit division whenever the product fits: the planner is instruction bound, profiles/r2_plan_decide_ncu.md)
+    off = (acc < 0x10000u && rounds < 0x10000u) ? (uint64_t)((uint32_t)acc * rounds / n) : acc * rounds / n;
   }
   return off + ((S - 1u) % (uint32_t)L) + nblk;
 }
@@ -183,8 +184,13 @@ TRPA_HD uint64_t band_setup_ops(int W, const PlanParams& pp) { return pp.setup +
 // duration classes inside a shape bucket (longest-processing-time-first order of the persistent launches)
 constexpr int kNumCls = 24;
 TRPA_HD uint32_t duration_class(uint64_t time) {
+  // l = floor(log2(time)) (0 for time <= 1)
+#ifdef __CUDA_ARCH__
+  const uint32_t l = time > 1u ? 63u - (uint32_t)__clzll((long long)time) : 0u;
+#else
   uint32_t l = 0;
   while (time > 1u) { time >>= 1; ++l; }
+#endif
   return l < 8u ? 0u : (l - 8u < (uint32_t)kNumCls ? l - 8u : (uint32_t)kNumCls - 1u);
 }
 

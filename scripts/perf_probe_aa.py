@@ -7,7 +7,7 @@ import rpa_b200
 ctx = rpa_b200.Context(0)
 rng = np.random.default_rng(1)
 aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
-for L, npairs in [(300, 200000), (100, 400000), (600, 50000)]:
+for L, npairs in [(300, 200000), (100, 400000), (600, 50000), (900, 25000)]:
     nseq = 1024
     seqs = [aa[rng.integers(0, 20, L)] for _ in range(nseq)]
     lens = np.full(nseq, L, np.uint32); off = (np.arange(nseq) * L).astype(np.uint64)

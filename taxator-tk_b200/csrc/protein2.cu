@@ -175,7 +175,8 @@ protein2_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __
   const int n = (int)A.len;  // columns (H)
   const int m = (int)B.len;  // rows (V)
   if (n > kP2MaxLen || m > kP2MaxLen) return;  // left to protein_kernel
-  if (skip_cols && p2h_takes(n, m)) return;    // done by protein2h_kernel
+  if (skip_cols == 1 && p2h_takes(n, m)) return;    // done by protein2h_kernel
+  if (skip_cols == 2 && n > 0 && m > 0) return;     // done by protein3_kernel (all pairs of up to 1000 x 1000)
   const uint8_t* a = residues + A.woff;
   const uint8_t* b = residues + B.woff;
   if (n == 0 || m == 0) {
@@ -368,9 +369,10 @@ cudaError_t launch_protein2(const PairDesc* pairs, u32 count, const SeqDesc* seq
     attr = true;
   }
   const bool half = protein_half_enabled();
+  const bool quarter = half && protein_quarter_enabled();
   if (half) {
-    e = protein_quarter_enabled() ? launch_protein3(pairs, count, seqs, residues, out2, max_len, aa_mask, stream)
-                                  : launch_h(pairs, count, seqs, residues, out2, stream);
+    e = quarter ? launch_protein3(pairs, count, seqs, residues, out2, max_len, aa_mask, stream)
+                : launch_h(pairs, count, seqs, residues, out2, stream);
     if (e != cudaSuccess) return e;
   }
   const u32 blocks = (count + kP2Warps - 1) / kP2Warps;
@@ -381,7 +383,9 @@ cudaError_t launch_protein2(const PairDesc* pairs, u32 count, const SeqDesc* seq
   // the strip templates round the columns per lane up to 4, 8, 10, 12 or 16
   const u32 cq = cols <= 4 ? 1u : (cols <= 8 ? 2u : (cols <= 12 ? 3u : 4u));
   const size_t smem = (size_t)kP2Warps * 27 * cq * 128 + 27 * 32;
-  protein2_kernel<<<blocks, 32 * kP2Warps, smem, stream>>>(pairs, count, seqs, residues, out2, scratch, scratch_stride, cq, half ? 1 : 0);
+  // with protein3 only the empty pairs are left for this kernel (pairs beyond 1000 residues: protein.cu)
+  protein2_kernel<<<blocks, 32 * kP2Warps, smem, stream>>>(pairs, count, seqs, residues, out2, scratch, scratch_stride, cq,
+                                                           quarter ? 2 : (half ? 1 : 0));
   return cudaGetLastError();
 }
 

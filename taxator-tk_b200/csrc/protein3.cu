@@ -1,10 +1,11 @@
-// Third-generation protein kernel for the short pairs (|A| <= 320 columns, |B| <= 1000 rows) that make up the
-// protein workloads: same result as protein2.cu / getAlignmentProtein (core/src/taxonpredictionmodelsequence.hh:173-242:
+// Third-generation protein kernel for all pairs of up to 1000 x 1000 residues (8 lanes per pair for |A| <= 320 columns,
+// the protein workloads of BASELINE.json; 16 lanes up to 640, a whole warp up to 1000): same result as protein2.cu /
+// getAlignmentProtein (core/src/taxonpredictionmodelsequence.hh:173-242:
 // BLOSUM62, linear gap -1, SeqAn tie order diagonal >= vertical >= horizontal, traced alignment length), same packed
 // 32-bit cell (score * 2^13 + priority * 2^11 + #gap columns of the traced path, see protein2.cu) and the same per-lane
 // query profile in shared memory (one conflict-free LDS.U8 per cell).  What changes is the shape of the wavefront:
 //   * EIGHT lanes per pair (four pairs per warp), up to 40 columns per lane: the ramp of the wavefront is 7 steps
-//     instead of 15 (half-warp kernel) or 31 (one warp per pair);
+//     instead of 15 (half-warp kernel) or 31 (one warp per pair); longer A: 16 or 32 lanes of up to 40 / 32 columns;
 //   * R rows per step (2 or 4), walked in SKEWED order -- cells (0,k), (1,k-1), (2,k-2), ... are adjacent in the
 //     instruction stream -- so every lane carries R independent max chains and the per-step bookkeeping (shuffles,
 //     predicates, row addresses) is paid once per R * C cells (160 at R = 4, C = 40; the half-warp kernel: 40);
@@ -19,9 +20,11 @@ namespace trpa {
 
 namespace {
 
-constexpr int kQLanes = 8;        // lanes per pair
-constexpr int kQMaxCols = 320;    // 8 lanes x 40 columns
-constexpr int kQMaxRows = 1000;   // the gap count must fit 11 bits: |A| + |B| <= 2047
+constexpr int kQMaxLen = 1000;    // the gap count must fit 11 bits: |A| + |B| <= 2047
+// a group of LANES lanes takes the pairs with lo(LANES) < |A| <= hi(LANES): 8 lanes up to 320 columns (40 per lane),
+// 16 lanes up to 640, 32 lanes up to 1000
+__host__ __device__ constexpr int q_lo(int lanes) { return lanes == 8 ? 0 : (lanes == 16 ? 320 : 640); }
+__host__ __device__ constexpr int q_hi(int lanes) { return lanes == 8 ? 320 : (lanes == 16 ? 640 : kQMaxLen); }
 constexpr int kQWarps = 1;        // warps per CTA (shared memory decides how many pairs are resident: finest granularity)
 
 constexpr int SH = 13;
@@ -48,7 +51,8 @@ cudaError_t ensure_table3() {
   return e;
 }
 
-__device__ __forceinline__ bool q_takes(int n, int m) { return n > 0 && m > 0 && n <= kQMaxCols && m <= kQMaxRows; }
+template <int LANES>
+__device__ __forceinline__ bool q_takes(int n, int m) { return n > q_lo(LANES) && n <= q_hi(LANES) && m > 0 && m <= kQMaxLen; }
 
 __device__ __forceinline__ int max3i(int a, int b, int c) { return max(max(a, b), c); }
 
@@ -59,15 +63,15 @@ __device__ __forceinline__ uint4 lds128(u32 addr) {
 }
 __device__ __forceinline__ void sts32(u32 addr, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
-// One pair on the 8 lanes of a quarter warp, C columns per lane, RIGHT aligned (the first 8 * C - n columns of the low
+// One pair on a group of LANES lanes, C columns per lane, RIGHT aligned (the first LANES * C - n columns of the low
 // lanes are padding: profile 0, row-0 value 0 -- the vertical candidate reproduces the left boundary column there, see
-// protein2.cu).  All four quarters of a warp run the same number of steps (the longest B of the four decides).
-template <int C, int R, int ALT>
+// protein2.cu).  All groups of a warp run the same number of steps (the longest B among them decides).
+template <int LANES, int C, int R, int ALT>
 __device__ __forceinline__ void protein3_run(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n, int m,
                                              bool mine, u32 prof_sa, u32 t2_sa, u32 lp, int steps, u32 mask, int one,
                                              int2* __restrict__ out2, u32 oidx) {
   constexpr int CQ = (C + 3) / 4;   // the profile keeps whole column quads; columns >= C of the last quad stay unused
-  const int pad = kQLanes * C - n;                // leading padding columns
+  const int pad = LANES * C - n;                  // leading padding columns
   const int v1 = (int)lp * C - pad;               // index of this lane's first column (may be < 0)
 
   // ---- profile[bb][q][lane][k] = e(a[v1 + 4q + k], bb): 16-byte rows of the symmetric table, transposed bytewise
@@ -134,7 +138,7 @@ __device__ __forceinline__ void protein3_run(const uint8_t* __restrict__ a, cons
   for (int t = 1; t <= steps; ++t) {
     int recv[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) recv[r] = __shfl_up_sync(0xffffffffu, last[r], 1, kQLanes);
+    for (int r = 0; r < R; ++r) recv[r] = __shfl_up_sync(0xffffffffu, last[r], 1, LANES);
     const int j = t - (int)lp;                    // this lane's row block at step t
     const int i0 = R * (j - 1) + 1;
     u32 bnext[R];
@@ -183,14 +187,14 @@ __device__ __forceinline__ void protein3_run(const uint8_t* __restrict__ a, cons
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         last[r] = left[r];
-        if (lp == kQLanes - 1 && i0 + r == m) res = left[r];
+        if (lp == LANES - 1 && i0 + r == m) res = left[r];
       }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) bcur[r] = bnext[r];
   }
   if (mine && (bad & 1u)) __trap();   // a residue the stores were said not to contain: fail loudly
-  if (lp == kQLanes - 1 && mine) {
+  if (lp == LANES - 1 && mine) {
     const int P = res - m * ROWBIAS;        // remove the per-row bias of the last row
     const int score = P >> SH;              // arithmetic shift: floor, low fields are non-negative
     const int gaps = P & 0x7ff;
@@ -198,7 +202,7 @@ __device__ __forceinline__ void protein3_run(const uint8_t* __restrict__ a, cons
   }
 }
 
-template <int R, int ALT>
+template <int LANES, int R, int ALT>
 __global__ void __launch_bounds__(32 * kQWarps, 1)
 protein3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __restrict__ seqs,
                 const uint8_t* __restrict__ residues, int2* __restrict__ out2, u32 cq_cap, u32 mask, int one) {
@@ -210,62 +214,103 @@ protein3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __
   for (int i = threadIdx.x; i < 64; i += blockDim.x)
     reinterpret_cast<uint4*>(t2)[i] = reinterpret_cast<const uint4*>(&c_prof_e[0][0])[i];
   __syncthreads();
-  const u32 lane = threadIdx.x & 31, lp = lane & 7u;
+  constexpr u32 G = 32u / LANES;   // pairs per warp
+  const u32 lane = threadIdx.x & 31, lp = lane & (u32)(LANES - 1);
   const u32 warp_in_cta = threadIdx.x >> 5;
   const u32 warp_gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const u32 pidx = warp_gid * 4u + (lane >> 3);
+  const u32 pidx = warp_gid * G + lane / (u32)LANES;
   int n = 0, m = 0;
   const uint8_t* a = residues;
   const uint8_t* b = residues;
   u32 oidx = 0;
-  bool mine = false;   // this quarter's pair is handled here
+  bool mine = false;   // this group's pair is handled here
   if (pidx < count) {
     const PairDesc pd = pairs[pidx];
     const SeqDesc A = seqs[pd.a], B = seqs[pd.b];
-    if (q_takes((int)A.len, (int)B.len)) {
+    if (q_takes<LANES>((int)A.len, (int)B.len)) {
       mine = true; n = (int)A.len; m = (int)B.len; oidx = pd.out;
       a = residues + A.woff; b = residues + B.woff;
     }
   }
   if (!__any_sync(0xffffffffu, mine)) return;
-  // all quarters use the lane width the widest pair needs and run as many steps as the longest one
+  // all groups use the lane width the widest pair needs and run as many steps as the longest one
   int nmax = n, mmax = m;
-  nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 8)); nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
-  mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, 8)); mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, 16));
-  const int cols = (nmax + kQLanes - 1) / kQLanes;
+#pragma unroll
+  for (int o = LANES; o < 32; o <<= 1) {
+    nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+    mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
+  }
+  const int cols = (nmax + LANES - 1) / LANES;
   if ((cols + 3) / 4 > (int)cq_cap) __trap();   // the launcher sized the profile from a wrong max_len: fail loudly
-  const int steps = (mmax + R - 1) / R + (kQLanes - 1);
+  const int steps = (mmax + R - 1) / R + (LANES - 1);
   const u32 prof_sa = (u32)__cvta_generic_to_shared(prof_all) + (warp_in_cta * (u32)__popc(mask) * cq_cap * 32u + lane) * 4u;
   const u32 t2_sa = (u32)__cvta_generic_to_shared(t2);
-  if (cols <= 8) protein3_run<8, R, ALT>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, one, out2, oidx);
-  else if (cols <= 16) protein3_run<16, R, ALT>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, one, out2, oidx);
-  else if (cols <= 24) protein3_run<24, R, ALT>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, one, out2, oidx);
-  else if (cols <= 32) protein3_run<32, R, ALT>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, one, out2, oidx);
-  else if (cols <= 36) protein3_run<36, R, ALT>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, one, out2, oidx);
-  else if (cols <= 38) protein3_run<38, R, ALT>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, one, out2, oidx);
-  else protein3_run<40, R, ALT>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, one, out2, oidx);
-}
-
-// 0 (default): four rows per step, every 3rd column in the fma-heavy form; A/B hooks: TRPA_PROTEIN_ROWS=2 (1: two rows,
-// plain cells), TRPA_PROTEIN_ALT=4 / 0 / 2 (2 / 3 / 4: four rows with every 4th / no / every 2nd column fma-heavy).
-// Measured on C3 (gpurun_out/r2_34): plain 34.0 ms of alignment per step, every 4th 33.2, every 3rd 33.0.
-int protein3_variant() {
-  static int v = -1;
-  if (v < 0) {
-    v = 0;
-    if (const char* e = getenv("TRPA_PROTEIN_ROWS")) if (e[0] == '2') v = 1;
-    if (const char* e = getenv("TRPA_PROTEIN_ALT")) { if (e[0] == '4') v = 2; else if (e[0] == '0') v = 3; else if (e[0] == '2') v = 4; }
+#define TRPA_P3_RUN(CC) protein3_run<LANES, CC, R, ALT>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, one, out2, oidx)
+  if (LANES == 8) {
+    if (cols <= 8) TRPA_P3_RUN(8);
+    else if (cols <= 16) TRPA_P3_RUN(16);
+    else if (cols <= 24) TRPA_P3_RUN(24);
+    else if (cols <= 32) TRPA_P3_RUN(32);
+    else if (cols <= 36) TRPA_P3_RUN(36);
+    else if (cols <= 38) TRPA_P3_RUN(38);
+    else TRPA_P3_RUN(40);
+  } else if (LANES == 16) {   // 321 .. 640 columns: 21 .. 40 per lane
+    if (cols <= 24) TRPA_P3_RUN(24);
+    else if (cols <= 32) TRPA_P3_RUN(32);
+    else if (cols <= 36) TRPA_P3_RUN(36);
+    else TRPA_P3_RUN(40);
+  } else {                    // 641 .. 1000 columns: 21 .. 32 per lane
+    if (cols <= 24) TRPA_P3_RUN(24);
+    else if (cols <= 28) TRPA_P3_RUN(28);
+    else TRPA_P3_RUN(32);
   }
-  return v;
+#undef TRPA_P3_RUN
 }
 
 }  // namespace
 
-bool protein3_takes(u32 n, u32 m) { return n > 0 && m > 0 && n <= (u32)kQMaxCols && m <= (u32)kQMaxRows; }
+bool protein3_takes(u32 n, u32 m) { return n > 0 && m > 0 && n <= (u32)kQMaxLen && m <= (u32)kQMaxLen; }
 
-// max_len: longest staged sequence of the launch (0 = unknown) -- sizes the shared-memory profile together with
-// aa_mask (residue ordinals that may occur, 0 = all 27): 20 residues x 40 columns per lane = 25.6 KB per warp, eight
-// warps = 32 pairs per SM; all 27: 34.6 KB, six warps
+// Cell mix of the build: four rows per step, every 3rd column in the fma-heavy form.  Measured on C3 against the other
+// mixes (gpurun_out/r2_34, r2_35; alignment time per step): plain cells 34.0 ms, every 4th column 33.2, every 3rd 33.0,
+// every 2nd 33.5; two rows per step with plain cells 34.8 ms.
+namespace {
+constexpr int kRows = 4, kAlt = 3;
+
+template <int LANES>
+cudaError_t launch_lanes(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues, int2* out2,
+                         u32 max_len, u32 mask, cudaStream_t stream) {
+  const u32 nrows = (u32)__builtin_popcount(mask);
+  const u32 longest = (max_len == 0 || max_len > (u32)q_hi(LANES)) ? (u32)q_hi(LANES) : max_len;
+  const u32 cols = (longest + LANES - 1) / LANES;
+  // the column counts the kernel is instantiated for, rounded up to whole quads
+  const u32 cq = cols <= 8 ? 2u : (cols <= 16 ? 4u : (cols <= 24 ? 6u : (cols <= 28 ? 7u : (cols <= 32 ? 8u : (cols <= 36 ? 9u : 10u)))));
+  const size_t smem = 1024 + (size_t)kQWarps * nrows * cq * 128;
+  auto kern = protein3_kernel<LANES, kRows, kAlt>;
+  static bool attr_set[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& attr = attr_set[dev & 15];   // the attributes are per device
+  if (!attr) {
+    const int cap = (int)(1024 + kQWarps * 27 * 10 * 128);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  constexpr u32 G = 32u / LANES;
+  const u32 warps = (count + G - 1u) / G;
+  const u32 blocks = (warps + kQWarps - 1) / kQWarps;
+  kern<<<blocks, 32 * kQWarps, smem, stream>>>(pairs, count, seqs, residues, out2, cq, mask, 1);
+  return cudaGetLastError();
+}
+}  // namespace
+
+// max_len: longest staged sequence of the launch (0 = unknown) -- decides which lane widths are launched at all and
+// sizes the shared-memory profile together with aa_mask (residue ordinals that may occur, 0 = all 27): 20 residues x
+// 40 columns per lane = 25.6 KB per warp, eight warps per SM; all 27: 34.6 KB, six warps.  Every launch walks the whole
+// pair list and takes the pairs of its column range.
 cudaError_t launch_protein3(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues, int2* out2,
                             u32 max_len, u32 aa_mask, cudaStream_t stream) {
   if (count == 0) return cudaSuccess;
@@ -273,31 +318,17 @@ cudaError_t launch_protein3(const PairDesc* pairs, u32 count, const SeqDesc* seq
   if (e != cudaSuccess) return e;
   u32 mask = aa_mask & 0x7ffffffu;
   if (mask == 0) mask = 0x7ffffffu;
-  const u32 nrows = (u32)__builtin_popcount(mask);
-  const u32 longest = (max_len == 0 || max_len > (u32)kQMaxCols) ? (u32)kQMaxCols : max_len;
-  const u32 cols = (longest + kQLanes - 1) / kQLanes;
-  const u32 cq = cols <= 8 ? 2u : (cols <= 16 ? 4u : (cols <= 24 ? 6u : (cols <= 32 ? 8u : (cols <= 36 ? 9u : 10u))));
-  const size_t smem = 1024 + (size_t)kQWarps * nrows * cq * 128;
-  typedef void (*Kern)(const PairDesc*, u32, const SeqDesc*, const uint8_t*, int2*, u32, u32, int);
-  static const Kern kerns[5] = {protein3_kernel<4, 3>, protein3_kernel<2, 0>, protein3_kernel<4, 4>, protein3_kernel<4, 0>, protein3_kernel<4, 2>};
-  const int variant = protein3_variant();
-  const Kern kern = kerns[variant];
-  static bool attr_set[16][5] = {{false}};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  bool& attr = attr_set[dev & 15][variant];   // the attributes are per device
-  if (!attr) {
-    const int cap = (int)(1024 + kQWarps * 27 * 10 * 128);
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+  e = launch_lanes<8>(pairs, count, seqs, residues, out2, max_len, mask, stream);
+  if (e != cudaSuccess) return e;
+  if (max_len == 0 || max_len > (u32)q_lo(16)) {
+    e = launch_lanes<16>(pairs, count, seqs, residues, out2, max_len, mask, stream);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (e != cudaSuccess) return e;
-    attr = true;
   }
-  const u32 warps = (count + 3u) / 4u;
-  const u32 blocks = (warps + kQWarps - 1) / kQWarps;
-  kern<<<blocks, 32 * kQWarps, smem, stream>>>(pairs, count, seqs, residues, out2, cq, mask, 1);
-  return cudaGetLastError();
+  if (max_len == 0 || max_len > (u32)q_lo(32)) {
+    e = launch_lanes<32>(pairs, count, seqs, residues, out2, max_len, mask, stream);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 }  // namespace trpa

@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_pipeline.py tests/test_gpu_golden.py tests/test_gpu_fuzz.py -m gpu -x -q -k "protein or aa or random_workload" 2>&1 | tail -2
 echo "== protein3 (8/16/32 lanes)"; python scripts/perf_probe_aa.py 2>&1 | tail -4
-echo "== half-warp + protein2"; TRPA_PROTEIN_QUARTER=0 python scripts/perf_probe_aa.py 2>&1 | tail -4
+echo "== half-warp + protein2"; python scripts/perf_probe_aa.py 2>&1 | tail -4
 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu-baseline --extras none > gpurun_out/r2_48_c3.json 2> gpurun_out/r2_48_c3.err
 python - <<PY
 import json

@@ -1,6 +1,6 @@
 // C ABI of the B200-native RPA hot path (include/taxator_rpa_b200.h) + the per-round driver:
 //   decide kernel (one thread per query segment, machine.h) -> stage kernel (pack.cu)
-//   -> shape bucketing -> edit-distance / protein kernels (myers3.cuh / protein2.cu) -> decide ...
+//   -> shape bucketing -> edit-distance / protein kernels (myers3.cuh / protein3.cu) -> decide ...
 // There is no CPU fallback: every compute entry point needs a CUDA device.
 // Compile with --fmad=false (decision arithmetic must match the reference's IEEE float/double ops).
 #include <algorithm>

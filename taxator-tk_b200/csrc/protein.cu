@@ -49,7 +49,7 @@ protein_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __r
   const uint8_t* b = residues + B.woff;
   const int n = (int)A.len;  // columns (H)
   const int m = (int)B.len;  // rows (V)
-  if (n <= skip_below && m <= skip_below) return;  // handled by protein2_kernel
+  if (n <= skip_below && m <= skip_below) return;  // handled by protein3_kernel
   int2* my_scratch = scratch + (size_t)warp_gid * scratch_stride;
 
   int res_s = 0, res_nd = 0;
@@ -119,9 +119,10 @@ protein_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __r
   if (lane == 0) out2[pd.out] = make_int2(res_s, res_nd);
 }
 
-cudaError_t launch_protein2(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,
-                            int2* out2, int2* scratch, u32 scratch_stride, u32 max_len, u32 aa_mask, cudaStream_t stream);
-int protein2_max_len();
+// protein3.cu: the packed-cell kernel for every pair of up to 1000 x 1000 residues (and the empty pairs)
+cudaError_t launch_protein3(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues, int2* out2,
+                            u32 max_len, u32 aa_mask, cudaStream_t stream);
+constexpr int kPackedMaxLen = 1000;
 
 // max_len: longest staged sequence of the launch (decides whether the 32-bit fallback kernel runs)
 cudaError_t launch_protein(const PairDesc* pairs, u32 count, const SeqDesc* seqs, const uint8_t* residues,
@@ -130,10 +131,10 @@ cudaError_t launch_protein(const PairDesc* pairs, u32 count, const SeqDesc* seqs
   cudaError_t e = ensure_table();
   if (e != cudaSuccess) return e;
   const u32 blocks = (count + 3) / 4;
-  e = launch_protein2(pairs, count, seqs, residues, out2, scratch, scratch_stride, max_len, aa_mask, stream);
+  e = launch_protein3(pairs, count, seqs, residues, out2, max_len, aa_mask, stream);
   if (e != cudaSuccess) return e;
-  if ((int)max_len > protein2_max_len()) {
-    protein_kernel<<<blocks, 128, 0, stream>>>(pairs, count, seqs, residues, out2, scratch, scratch_stride, protein2_max_len());
+  if ((int)max_len > kPackedMaxLen) {
+    protein_kernel<<<blocks, 128, 0, stream>>>(pairs, count, seqs, residues, out2, scratch, scratch_stride, kPackedMaxLen);
     return cudaGetLastError();
   }
   return cudaSuccess;

@@ -1,16 +1,28 @@
-// Third-generation protein kernel for all pairs of up to 1000 x 1000 residues (8 lanes per pair for |A| <= 320 columns,
-// the protein workloads of BASELINE.json; 16 lanes up to 640, a whole warp up to 1000): same result as protein2.cu /
-// getAlignmentProtein (core/src/taxonpredictionmodelsequence.hh:173-242:
-// BLOSUM62, linear gap -1, SeqAn tie order diagonal >= vertical >= horizontal, traced alignment length), same packed
-// 32-bit cell (score * 2^13 + priority * 2^11 + #gap columns of the traced path, see protein2.cu) and the same per-lane
-// query profile in shared memory (one conflict-free LDS.U8 per cell).  What changes is the shape of the wavefront:
-//   * EIGHT lanes per pair (four pairs per warp), up to 40 columns per lane: the ramp of the wavefront is 7 steps
-//     instead of 15 (half-warp kernel) or 31 (one warp per pair); longer A: 16 or 32 lanes of up to 40 / 32 columns;
-//   * R rows per step (2 or 4), walked in SKEWED order -- cells (0,k), (1,k-1), (2,k-2), ... are adjacent in the
-//     instruction stream -- so every lane carries R independent max chains and the per-step bookkeeping (shuffles,
-//     predicates, row addresses) is paid once per R * C cells (160 at R = 4, C = 40; the half-warp kernel: 40);
+// Protein kernel for all pairs of up to 1000 x 1000 residues: the result of getAlignmentProtein
+// (core/src/taxonpredictionmodelsequence.hh:173-242: BLOSUM62, linear gap -1, SeqAn tie order diagonal >= vertical >=
+// horizontal, dp_formula_linear.h:62-105 / dp_formula.h:152-163, traced alignment length hh:215-228).
+//
+// Each DP cell is ONE packed 32-bit integer
+//     P = score * 2^13 + priority * 2^11 + #gap columns on the traced path
+// so that a single signed max3 picks the best score and, on ties, SeqAn's priority (diagonal 2, vertical 1, horizontal
+// 0); the priority field is cleared before the value is stored.  The traced length follows from the gap count:
+// len = (|A| + |B| + #gaps) / 2.  Substitution scores come from a per-lane "query profile" in shared memory,
+// profile[b][c/4][lane][c%4] = 2*BLOSUM62(a_c, b) + 9 (uint8; bank == lane for every access: one conflict-free LDS.U8 per
+// cell), so the diagonal candidate is one multiply-add: D = profile * 2^12 + diag (= score + sub, priority 2, plus a
+// constant 2^15 that is carried as a per-row bias i*2^15 on every stored value, so the table stays unsigned and needs no
+// sign extension).  Valid while the gap count fits 11 bits: |A| + |B| <= 2047, i.e. both sequences <= 1000 residues
+// (longer pairs: the 32-bit-per-field kernel of protein.cu).  Per cell: 1 LDS.U8 + 1 IMAD + 2 VIADDMNMX + 1 LOP3.
+//
+// Shape of the wavefront (round 2; round 1 ran one warp or half a warp per pair, two rows per step):
+//   * EIGHT lanes per pair (four pairs per warp) for |A| <= 320, up to 40 columns per lane: the ramp of the wavefront is 7
+//     steps instead of 15 or 31; 16 lanes for 321-640 columns, a whole warp for 641-1000;
+//   * R = 4 rows per step, walked in SKEWED order -- cells (0,k), (1,k-1), (2,k-2), (3,k-3) are adjacent in the
+//     instruction stream -- so every lane carries four independent max chains and the per-step bookkeeping (shuffles,
+//     predicates, row addresses) is paid once per R * C cells (160 at C = 40);
 //   * the profile of a pair is built from 16-byte rows of the (symmetric) substitution table with byte transposes
-//     (8 PRMT + 4 STS.32 per 16 entries) instead of one table look-up per entry.
+//     (8 PRMT + 4 STS.32 per 16 entries) and keeps rows only for the residues that occur in the stores;
+//   * every third column computes both additions as IMAD on the fma pipe and takes one VIMNMX3 (2 instead of 3 alu-pipe
+//     instructions, one more issue slot): the alu pipe and the issue slots are loaded evenly.
 #include "common.cuh"
 #include "launch.h"
 #include "blosum62_table.h"
@@ -34,7 +46,7 @@ constexpr int CV = -(1 << SH) + (1 << 11) + 1 + ROWBIAS;      // vertical: score
 constexpr int CH = -(1 << SH) + 1;                            // horizontal: score-1, priority 0, +1 gap
 constexpr int BND = -(1 << SH) + 1;                           // boundary(k) = k * BND: score -k after k gap columns
 
-// e[r][b] = 2 * BLOSUM62(r, b) + 9 (the unsigned profile entry of protein2.cu); rows / columns 27..31 are 0 = the
+// e[r][b] = 2 * BLOSUM62(r, b) + 9 (the unsigned profile entry); rows / columns 27..31 are 0 = the
 // profile of a padding column
 __device__ __align__(16) uint8_t c_prof_e[32][32];   // read once per CTA with two coalesced 16-byte loads per lane
 bool g_loaded3[16] = {false};
@@ -64,8 +76,10 @@ __device__ __forceinline__ uint4 lds128(u32 addr) {
 __device__ __forceinline__ void sts32(u32 addr, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
 // One pair on a group of LANES lanes, C columns per lane, RIGHT aligned (the first LANES * C - n columns of the low
-// lanes are padding: profile 0, row-0 value 0 -- the vertical candidate reproduces the left boundary column there, see
-// protein2.cu).  All groups of a warp run the same number of steps (the longest B among them decides).
+// lanes are padding: profile 0 (= substitution -4.5) for every residue and row-0 value 0, so neither the diagonal nor the
+// horizontal candidate can win there and the vertical candidate reproduces the left boundary column value (-i, i gaps)
+// in every padding cell -- the first real column sees exactly the boundary it needs; no per-cell predicates).  All
+// groups of a warp run the same number of steps (the longest B among them decides).
 template <int LANES, int C, int R, int ALT>
 __device__ __forceinline__ void protein3_run(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n, int m,
                                              bool mine, u32 prof_sa, u32 t2_sa, u32 lp, int steps, u32 mask, int one,
@@ -230,6 +244,8 @@ protein3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __
     if (q_takes<LANES>((int)A.len, (int)B.len)) {
       mine = true; n = (int)A.len; m = (int)B.len; oidx = pd.out;
       a = residues + A.woff; b = residues + B.woff;
+    } else if (LANES == 8 && lp == 0 && (A.len == 0 || B.len == 0) && A.len <= (u32)kQMaxLen && B.len <= (u32)kQMaxLen) {
+      out2[pd.out] = make_int2(-(int)(A.len + B.len), 0);   // an empty side: all gaps, nothing traced diagonally
     }
   }
   if (!__any_sync(0xffffffffu, mine)) return;

@@ -820,7 +820,7 @@ def main():
                                        "counts as 32 columns, and blocks of re-run attempts (band_retries) are included",
                 "kernel_ms_per_step": k_ms / args.steps, "kernel_share_of_step": (k_ms / args.steps) / ms_step}
     if fd.protein and peak:
-        roofline["frac_r01_constant"] = roofline["frac"] * ALU_OPS_PER_CELL_AA / 3.0   # against lane-ops/s / 3 (round 1)
+        roofline["frac_r01_constant"] = roofline["frac"] * 3.0 / ALU_OPS_PER_CELL_AA   # against lane-ops/s / 3 (round 1)
     if not fd.protein and peak:
         roofline["frac_r01_constant"] = roofline["frac"] * ALU_OPS_PER_WORDSTEP_R01 / ALU_OPS_PER_WORDSTEP
         # Round 2 narrows the wedge further (fewer executed cells for the same integers), which LOWERS `frac` (per-step

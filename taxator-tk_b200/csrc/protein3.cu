@@ -63,6 +63,13 @@ cudaError_t ensure_table3() {
   return e;
 }
 
+// columns per lane the kernel is instantiated for: what `cols` columns per lane are rounded up to (the host sizes the
+// shared-memory profile with the same function)
+__host__ __device__ constexpr int q_round_cols(int lanes, int cols) {
+  return lanes == 8 ? (cols <= 8 ? 8 : cols <= 16 ? 16 : cols <= 24 ? 24 : cols <= 32 ? 32 : cols <= 36 ? 36 : cols <= 38 ? 38 : 40)
+       : lanes == 16 ? (cols <= 24 ? 24 : cols <= 32 ? 32 : cols <= 36 ? 36 : 40)
+                     : (cols <= 24 ? 24 : cols <= 28 ? 28 : 32);
+}
 template <int LANES>
 __device__ __forceinline__ bool q_takes(int n, int m) { return n > q_lo(LANES) && n <= q_hi(LANES) && m > 0 && m <= kQMaxLen; }
 
@@ -225,9 +232,6 @@ protein3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __
   extern __shared__ __align__(16) unsigned char smem3[];
   unsigned char* t2 = smem3;                                      // e[32][32]
   unsigned char* prof_all = smem3 + 1024;                         // [warp][bb][q][lane][4]
-  for (int i = threadIdx.x; i < 64; i += blockDim.x)
-    reinterpret_cast<uint4*>(t2)[i] = reinterpret_cast<const uint4*>(&c_prof_e[0][0])[i];
-  __syncthreads();
   constexpr u32 G = 32u / LANES;   // pairs per warp
   const u32 lane = threadIdx.x & 31, lp = lane & (u32)(LANES - 1);
   const u32 warp_in_cta = threadIdx.x >> 5;
@@ -248,7 +252,12 @@ protein3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __
       out2[pd.out] = make_int2(-(int)(A.len + B.len), 0);   // an empty side: all gaps, nothing traced diagonally
     }
   }
+  // (a CTA is one warp: a launch that walks a pair list without pairs of its column range costs a few loads per CTA)
+  static_assert(kQWarps == 1, "the early exit below is per warp");
   if (!__any_sync(0xffffffffu, mine)) return;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x)
+    reinterpret_cast<uint4*>(t2)[i] = reinterpret_cast<const uint4*>(&c_prof_e[0][0])[i];
+  __syncthreads();
   // all groups use the lane width the widest pair needs and run as many steps as the longest one
   int nmax = n, mmax = m;
 #pragma unroll
@@ -256,28 +265,28 @@ protein3_kernel(const PairDesc* __restrict__ pairs, u32 count, const SeqDesc* __
     nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
     mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
   }
-  const int cols = (nmax + LANES - 1) / LANES;
+  const int cols = q_round_cols(LANES, (nmax + LANES - 1) / LANES);
   if ((cols + 3) / 4 > (int)cq_cap) __trap();   // the launcher sized the profile from a wrong max_len: fail loudly
   const int steps = (mmax + R - 1) / R + (LANES - 1);
   const u32 prof_sa = (u32)__cvta_generic_to_shared(prof_all) + (warp_in_cta * (u32)__popc(mask) * cq_cap * 32u + lane) * 4u;
   const u32 t2_sa = (u32)__cvta_generic_to_shared(t2);
 #define TRPA_P3_RUN(CC) protein3_run<LANES, CC, R, ALT>(a, b, n, m, mine, prof_sa, t2_sa, lp, steps, mask, one, out2, oidx)
   if (LANES == 8) {
-    if (cols <= 8) TRPA_P3_RUN(8);
-    else if (cols <= 16) TRPA_P3_RUN(16);
-    else if (cols <= 24) TRPA_P3_RUN(24);
-    else if (cols <= 32) TRPA_P3_RUN(32);
-    else if (cols <= 36) TRPA_P3_RUN(36);
-    else if (cols <= 38) TRPA_P3_RUN(38);
+    if (cols == 8) TRPA_P3_RUN(8);
+    else if (cols == 16) TRPA_P3_RUN(16);
+    else if (cols == 24) TRPA_P3_RUN(24);
+    else if (cols == 32) TRPA_P3_RUN(32);
+    else if (cols == 36) TRPA_P3_RUN(36);
+    else if (cols == 38) TRPA_P3_RUN(38);
     else TRPA_P3_RUN(40);
   } else if (LANES == 16) {   // 321 .. 640 columns: 21 .. 40 per lane
-    if (cols <= 24) TRPA_P3_RUN(24);
-    else if (cols <= 32) TRPA_P3_RUN(32);
-    else if (cols <= 36) TRPA_P3_RUN(36);
+    if (cols == 24) TRPA_P3_RUN(24);
+    else if (cols == 32) TRPA_P3_RUN(32);
+    else if (cols == 36) TRPA_P3_RUN(36);
     else TRPA_P3_RUN(40);
   } else {                    // 641 .. 1000 columns: 21 .. 32 per lane
-    if (cols <= 24) TRPA_P3_RUN(24);
-    else if (cols <= 28) TRPA_P3_RUN(28);
+    if (cols == 24) TRPA_P3_RUN(24);
+    else if (cols == 28) TRPA_P3_RUN(28);
     else TRPA_P3_RUN(32);
   }
 #undef TRPA_P3_RUN
@@ -298,9 +307,8 @@ cudaError_t launch_lanes(const PairDesc* pairs, u32 count, const SeqDesc* seqs, 
                          u32 max_len, u32 mask, cudaStream_t stream) {
   const u32 nrows = (u32)__builtin_popcount(mask);
   const u32 longest = (max_len == 0 || max_len > (u32)q_hi(LANES)) ? (u32)q_hi(LANES) : max_len;
-  const u32 cols = (longest + LANES - 1) / LANES;
-  // the column counts the kernel is instantiated for, rounded up to whole quads
-  const u32 cq = cols <= 8 ? 2u : (cols <= 16 ? 4u : (cols <= 24 ? 6u : (cols <= 28 ? 7u : (cols <= 32 ? 8u : (cols <= 36 ? 9u : 10u)))));
+  // profile capacity: the column count the kernel rounds the launch's widest pair up to, in whole quads
+  const u32 cq = ((u32)q_round_cols(LANES, (int)((longest + LANES - 1) / LANES)) + 3u) / 4u;
   const size_t smem = 1024 + (size_t)kQWarps * nrows * cq * 128;
   auto kern = protein3_kernel<LANES, kRows, kAlt>;
   static bool attr_set[16] = {false};

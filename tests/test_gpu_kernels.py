@@ -89,22 +89,27 @@ def test_edit_distance_lowercase_and_iupac(ctx):
     assert got.tolist() == want
 
 
-def test_protein_align(ctx):
-    rng = np.random.default_rng(5)
+@pytest.mark.parametrize("maxlen", [1100, 700, 430, 90])
+def test_protein_align(ctx, maxlen):
+    """maxlen: longest sequence of the batch -- the kernels size their shared-memory profile from it, per lane width
+    (8 / 16 / 32 lanes per pair)."""
+    rng = np.random.default_rng(5 + maxlen)
     O = ol.oracle()
     full = np.frombuffer(b"ABCDEFGHIJKLMNOPQRSTUVWYZX*", np.uint8)
     aa20 = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
+    lens_all = [1, 2, 5, 31, 32, 33, 100, 299, 300, 301, 321, 330, 400, 420, 511, 512, 513, 600, 641, 650, 1100]
     seqs, pa, pb = [], [], []
-    for t in range(500):
+    for t in range(500 if maxlen == 1100 else 200):
         alpha = full if t % 4 == 0 else aa20
-        L = int(rng.choice([1, 2, 5, 31, 32, 33, 100, 299, 300, 301, 400, 511, 512, 513, 600, 1100]))
+        L = int(rng.choice([x for x in lens_all if x <= maxlen]))
         a = alpha[rng.integers(0, len(alpha), L)].tobytes()
         if t % 2:
             b = _mutate(rng, a, float(rng.choice([0.0, 0.1, 0.4, 0.8])), alpha)
             if len(b) == 0:
                 b = b"A"
         else:
-            b = alpha[rng.integers(0, len(alpha), int(rng.integers(1, 700)))].tobytes()
+            b = alpha[rng.integers(0, len(alpha), int(rng.integers(1, min(700, maxlen) + 1)))].tobytes()
+        b = b[:maxlen]
         seqs += [a, b]
         pa.append(len(seqs) - 2); pb.append(len(seqs) - 1)
     chars, off, ln = _table(seqs)

@@ -269,11 +269,19 @@ __global__ void stage_aa_kernel(const StageReq* __restrict__ reqs, u32 n_req, co
     const SeqDesc d = descs[rq.desc];
     const u32* sp = rq.store ? r_packed + r_woff[rq.seq] : q_packed + q_woff[rq.seq];
     int self = 0;
-    for (u32 k = lane; k < d.len; k += 32) {
-      const u32 idx = rq.begin + k;
-      const u32 code = (sp[idx / 6] >> (5 * (idx % 6))) & 31u;
-      out[(u64)d.woff + k] = (uint8_t)code;
-      self += c_blosum[code][code];
+    // BLOSUM62(x, x) of ordinal `lane` sits in lane `lane`: one shuffle per residue instead of a constant-memory
+    // load whose address differs from lane to lane (serialised by the constant cache)
+    const int diag = lane < 27 ? (int)c_blosum[lane][lane] : 0;
+    const u32 rounds = (d.len + 31u) >> 5;
+    for (u32 it = 0; it < rounds; ++it) {
+      const u32 k = it * 32u + lane;
+      u32 code = 31u;
+      if (k < d.len) {
+        const u32 idx = rq.begin + k;
+        code = (sp[idx / 6] >> (5 * (idx % 6))) & 31u;
+        out[(u64)d.woff + k] = (uint8_t)code;
+      }
+      self += __shfl_sync(0xffffffffu, diag, code);   // lanes past the end read lane 31: 0
     }
     self = __reduce_add_sync(0xffffffffu, self);
     if (lane == 0) { descs[rq.desc].pad = (u32)self; descs[rq.desc].flags = 0; }

@@ -198,13 +198,21 @@ struct trpa_ctx {
 namespace trpa {
 
 // ------------------------------------------------------------------------------------ kernels
-__global__ void decide_kernel(Batch B, u32 seg_begin, u32 seg_end) {
-  const u32 s = seg_begin + blockIdx.x * blockDim.x + threadIdx.x;
+// per_warp: segments (= working lanes, spread evenly) per warp.  The threads of a warp follow different paths through
+// predict()'s loops and serialise each other's chains of dependent loads (ncu: 1.96 active threads per executed warp
+// instruction with 32 segments per warp); fewer segments per warp trade idle lanes for independent instruction streams.
+__global__ void __launch_bounds__(64, 12) decide_kernel(Batch B, u32 seg_begin, u32 seg_end, u32 per_warp) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 stride = 32u / per_warp, lane = t & 31u;
+  if (lane % stride) return;
+  const u32 s = seg_begin + (t >> 5) * per_warp + lane / stride;
   if (s >= seg_end) return;
   if (B.st[s].phase == PH_DONE) return;
-  Machine M(B, s);
+  SegState st = B.st[s];   // one copy in, one copy out instead of a global access per field
+  Machine M(B, s, st);
   M.advance();
-  if (B.st[s].phase != PH_DONE) atomicAdd(&B.counters[CN_ACTIVE], 1u);
+  B.st[s] = st;
+  if (st.phase != PH_DONE) atomicAdd(&B.counters[CN_ACTIVE], 1u);
 }
 
 __global__ void init_state_kernel(SegState* st, u32 n) {
@@ -873,7 +881,19 @@ enum PipeState { PS_IDLE = 0, PS_WAIT_DECIDE, PS_WAIT_PLAN, PS_DONE };
 // decide kernel of the pipe's chunk + read-back of the round counters (asynchronous)
 static int enqueue_decide(trpa_ctx* c, Pipe& P) {
   const int ev = begin_event(P, EV_DECIDE);
-  decide_kernel<<<(P.se - P.sb + 63) / 64, 64, 0, P.stream>>>(P.B, P.sb, P.se);
+  {
+    // Segments per warp: as few as still fit the chunk into ONE wave of warps (24 resident warps per SM at the
+    // kernel's register count).  Measured (gpurun_out/r2_54): C1, 1 k segments: 32 per warp 1.04 ms of decide per step,
+    // 1 per warp 0.50 ms; C3 / C2 (50 k / 100 k segments) want all 32 lanes (8 per warp: +8 % / +12 % decide time).
+    static const int forced = [] { const char* e = getenv("TRPA_DECIDE_PER_WARP"); const int v = e ? atoi(e) : 0;
+                                   return (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 0; }();
+    const u32 n = P.se - P.sb, wave = (u32)c->num_sms * 24u;
+    u32 per_warp = 1;
+    while (per_warp < 32u && (n + per_warp - 1) / per_warp > wave) per_warp *= 2u;
+    if (forced) per_warp = (u32)forced;
+    const u32 warps = (n + per_warp - 1) / per_warp;
+    decide_kernel<<<(warps + 1) / 2, 64, 0, P.stream>>>(P.B, P.sb, P.se, per_warp);
+  }
   CK(cudaGetLastError());
   end_event(P, ev);
   c->prof.launches_decide++;

@@ -136,6 +136,11 @@ struct Machine {
   TRPA_HD Machine(const Batch& b, uint32_t seg)
       : B(b), s(seg), S(b.st[seg]), rec(b.cands + b.segs[seg].cand_begin), qd(b.qd + b.segs[seg].cand_begin),
         qsim(b.qsim + b.segs[seg].cand_begin), fl(b.cflags + b.segs[seg].cand_begin) {}
+  // the segment's state in a caller-owned copy (the decide kernel keeps it in registers / local memory for the round
+  // and writes it back once)
+  TRPA_HD Machine(const Batch& b, uint32_t seg, SegState& state)
+      : B(b), s(seg), S(state), rec(b.cands + b.segs[seg].cand_begin), qd(b.qd + b.segs[seg].cand_begin),
+        qsim(b.qsim + b.segs[seg].cand_begin), fl(b.cflags + b.segs[seg].cand_begin) {}
 
   // ---- segment coordinates: hh:856-880 + store clipping (sequencestorage.hh:353, faidx.h:325-331)
   TRPA_HD void stage_candidate(uint32_t i) {

@@ -393,8 +393,12 @@ static int launch_myers_shapes3(trpa_ctx* c, Pipe& P, const u32* h_hist, const P
               shape_hasn(jobs[j].shape) ? "N" : "", jobs[j].cnt);
     fprintf(stderr, "\n");
   }
-  // largest buckets first
-  std::sort(jobs, jobs + nj, [](const Job& x, const Job& y) { return x.cnt > y.cnt; });
+  // SMALLEST buckets first: the big bucket's persistent launch takes every CTA slot of the GPU, a small latency-bound
+  // bucket (1-180 CTAs, 0.6-0.9 ms on its own) launched behind it only starts in its tail and ends the round late;
+  // launched first it runs beside the big one (C2: 331.8 -> 328.5 ms per step, C4 neutral; TRPA_SHAPE_ORDER=desc: A/B hook)
+  static const bool asc = [] { const char* e = getenv("TRPA_SHAPE_ORDER"); return !(e && e[0] == 'd'); }();
+  if (asc) std::sort(jobs, jobs + nj, [](const Job& x, const Job& y) { return x.cnt < y.cnt; });
+  else std::sort(jobs, jobs + nj, [](const Job& x, const Job& y) { return x.cnt > y.cnt; });
   const bool fork = nj > 1;
   if (fork) {
     if (!P.fork_ev) {

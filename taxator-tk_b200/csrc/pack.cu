@@ -304,7 +304,12 @@ __global__ void selfscore_kernel(SeqDesc* __restrict__ descs, u32 n, const uint8
   for (u32 s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n; s += warps) {
     const SeqDesc d = descs[s];
     int self = 0;
-    for (u32 k = lane; k < d.len; k += 32) { const u32 c = residues[(u64)d.woff + k]; self += c_blosum[c][c]; }
+    const int diag = lane < 27 ? (int)c_blosum[lane][lane] : 0;   // BLOSUM62(x, x) of ordinal `lane` (see stage_aa_kernel)
+    for (u32 it = 0; it * 32u < d.len; ++it) {
+      const u32 k = it * 32u + lane;
+      const u32 c = k < d.len ? (u32)residues[(u64)d.woff + k] : 31u;
+      self += __shfl_sync(0xffffffffu, diag, c);
+    }
     self = __reduce_add_sync(0xffffffffu, self);
     if (lane == 0) descs[s].pad = (u32)self;
   }

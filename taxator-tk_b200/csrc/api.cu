@@ -258,8 +258,15 @@ __global__ void scatter3_kernel(const PairDesc* pairs, u32 n, u32* hist, PairDes
   for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const PairDesc p = pairs[k];
     const u32 cls = p.cls < (u32)kNumCls ? p.cls : (u32)kNumCls - 1u;
-    const u32 pos = atomicAdd(&cur[(p.pad & 0xffu) * kNumCls + cls], 1u);   // pad: shape | k0 << 8
-    sorted[pos] = p;
+    const u32 key = (p.pad & 0xffu) * kNumCls + cls;   // pad: shape | k0 << 8
+    // one atomic per distinct (shape, class) of the warp: most pairs of a round share a handful of keys
+    const u32 active = __activemask();
+    const u32 same = __match_any_sync(active, key);
+    const u32 leader = __ffs(same) - 1u, lane = threadIdx.x & 31u;
+    u32 base = 0;
+    if (lane == leader) base = atomicAdd(&cur[key], (u32)__popc(same));
+    base = __shfl_sync(same, base, leader);
+    sorted[base + __popc(same & ((1u << lane) - 1u))] = p;
   }
 }
 // SortFilter on the device (core/src/alignmentsfilter.hh:171-190: stable sort, descending (score,

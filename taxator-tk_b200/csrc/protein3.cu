@@ -70,6 +70,15 @@ __host__ __device__ constexpr int q_round_cols(int lanes, int cols) {
        : lanes == 16 ? (cols <= 24 ? 24 : cols <= 32 ? 32 : cols <= 36 ? 36 : 40)
                      : (cols <= 24 ? 24 : cols <= 28 ? 28 : 32);
 }
+constexpr bool q_round_cols_covers() {   // every admissible column count is rounded UP to an instantiated one
+  for (int lanes = 8; lanes <= 32; lanes *= 2)
+    for (int n = q_lo(lanes) + 1; n <= q_hi(lanes); ++n) {
+      const int cols = (n + lanes - 1) / lanes, r = q_round_cols(lanes, cols);
+      if (r < cols || r > 40 || (r + 3) / 4 > 10) return false;
+    }
+  return true;
+}
+static_assert(q_round_cols_covers(), "protein3: column rounding does not cover the lane width's range");
 template <int LANES>
 __device__ __forceinline__ bool q_takes(int n, int m) { return n > q_lo(LANES) && n <= q_hi(LANES) && m > 0 && m <= kQMaxLen; }
 
